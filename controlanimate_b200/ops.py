@@ -1,0 +1,231 @@
+"""Tensor-level wrappers over the C ABI: torch is used for device memory and streams only.
+
+Every function validates what the kernels assume, passes raw `data_ptr()`s and the current CUDA
+stream, and raises (ValueError for contract violations, RuntimeError for CUDA/library failures).
+There is no CPU or eager fallback: a non-CUDA tensor is an error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+_DTYPES = {torch.bfloat16: L.CA_BF16, torch.float16: L.CA_F16, torch.float32: L.CA_F32}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise ValueError(f"unsupported dtype {t.dtype}") from None
+
+
+def _cuda(*ts: Optional[torch.Tensor]):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise ValueError("controlanimate_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t: Optional[torch.Tensor], n: Optional[int] = None) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    t = t.detach()
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.float().contiguous()
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes: int, device) -> Optional[torch.Tensor]:
+    if nbytes == 0:
+        return None
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def video_layout(x: torch.Tensor) -> int:
+    """Classify a [b,c,f,h,w] tensor: NCFHW-contiguous or BFHWC (native) strides."""
+    if x.dim() != 5:
+        raise ValueError(f"expected a 5-D [b,c,f,h,w] tensor, got {tuple(x.shape)}")
+    if x.is_contiguous():
+        return L.CA_LAYOUT_NCFHW
+    if x.permute(0, 2, 3, 4, 1).is_contiguous():
+        return L.CA_LAYOUT_BFHWC
+    raise ValueError("video tensor must be NCFHW-contiguous or BFHWC (b,f,h,w,c memory order)")
+
+
+def groupnorm_silu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, *,
+                   per_frame: bool = True, silu: bool = True, temb: Optional[torch.Tensor] = None,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = SiLU(GroupNorm(x + temb[:, :, None, None, None])) for x [b,c,f,h,w] in either layout (kernel 2)."""
+    _cuda(x, gamma, beta, temb)
+    layout = video_layout(x)
+    b, c, f, h, w = x.shape
+    y = torch.empty_like(x) if out is None else out  # empty_like preserves the (dense) strides
+    if y.shape != x.shape or y.stride() != x.stride() or y.dtype != x.dtype:
+        raise ValueError("out must match x in shape, strides and dtype")
+    g32, b32, t32 = _f32(gamma), _f32(beta), _f32(temb)
+    if g32.numel() != c or b32.numel() != c or (t32 is not None and tuple(t32.shape) != (b, c)):
+        raise ValueError("gamma/beta must be [c] and temb [b, c]")
+    lib = L.load()
+    nws = lib.ca_groupnorm_workspace_bytes(b, c, f, h, w, groups, int(per_frame), layout, _dt(x))
+    ws = _workspace(nws, x.device)
+    L.check(lib.ca_groupnorm_silu(x.data_ptr(), y.data_ptr(), g32.data_ptr(), b32.data_ptr(), _ptr(t32), b, c, f, h, w,
+                                  groups, float(eps), int(per_frame), int(silu), layout, _dt(x), _ptr(ws),
+                                  0 if ws is None else ws.numel(), _stream()), "ca_groupnorm_silu")
+    return y
+
+
+def layernorm_pe(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, *,
+                 pe: Optional[torch.Tensor] = None, frames: int = 1, sites: int = 1,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LayerNorm over the last dim of token-major x [..., c] (+ pe[frame(t)] with t = (b*f+frame)*sites+site)."""
+    _cuda(x, gamma, beta, pe)
+    if not x.is_contiguous():
+        raise ValueError("layernorm_pe: x must be contiguous token-major")
+    c = x.shape[-1]
+    rows = x.numel() // c
+    y = torch.empty_like(x) if out is None else out
+    g32, b32, pe32 = _f32(gamma), _f32(beta), _f32(pe)
+    if pe32 is not None:
+        pe32 = pe32.reshape(-1, c)
+        if pe32.shape[0] < frames:
+            raise ValueError(f"video has {frames} frames but the positional encoding only {pe32.shape[0]} (motion_module.py:236)")
+        if rows % (frames * sites) != 0:
+            raise ValueError("rows must be b*frames*sites")
+    L.check(L.load().ca_layernorm_pe(x.data_ptr(), y.data_ptr(), g32.data_ptr(), b32.data_ptr(), _ptr(pe32), rows, c,
+                                     frames, sites, float(eps), _dt(x), _stream()), "ca_layernorm_pe")
+    return y
+
+
+def temporal_attention_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, batch: int, frames: int, sites: int,
+                            heads: int, scale: Optional[float] = None, seq_major: bool = False,
+                            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(q k^T scale) v over the frame axis for q/k/v [(b f d), C] row matrices (kernel 1a).
+
+    Rows are token-major (t = (b*f+frame)*d+site) or, with seq_major, the reference's "(b d) f c" order.
+    q/k/v may be column slices of one packed [T, 3C] buffer (row stride 3C).
+    """
+    _cuda(q, k, v)
+    T, Cq = q.shape
+    if T != batch * frames * sites or k.shape != q.shape or v.shape != q.shape:
+        raise ValueError("q/k/v must be [(b*f*d), C] with identical shapes")
+    if Cq % heads:
+        raise ValueError("C must be divisible by heads")
+    for t in (q, k, v):
+        if t.stride(1) != 1:
+            raise ValueError("q/k/v rows must be dense")
+    hd = Cq // heads
+    o = torch.empty((T, Cq), dtype=q.dtype, device=q.device) if out is None else out
+    if o.stride(1) != 1 or o.shape != q.shape:
+        raise ValueError("bad out tensor")
+    scale = hd ** -0.5 if scale is None else scale
+    L.check(L.load().ca_temporal_attn_core(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), batch, frames, sites,
+                                           heads, hd, q.stride(0), k.stride(0), v.stride(0), o.stride(0), int(seq_major),
+                                           float(scale), _dt(q), _stream()), "ca_temporal_attn_core")
+    return o
+
+
+def residual_merge(per_net: Sequence[Sequence[torch.Tensor]], scales: Sequence[Sequence[float]], dst: Sequence[torch.Tensor], *,
+                   frames: int, add_into_dst: bool, layout: int) -> None:
+    """dst_i (=|+=) Σ_k scales[k][i] * per_net[k][i] in one launch (kernel 3).
+
+    layout NCFHW: per_net[k][i] is [(b f), c, h, w] contiguous, dst_i [b, c, f, h, w] contiguous.
+    layout BFHWC: per_net[k][i] is [(b f), c, h, w] channels_last, dst_i [b,c,f,h,w] with BFHWC strides
+                  (or a 4-D channels_last [(b f), c, h, w] tensor).
+    """
+    n_nets, n_res = len(per_net), len(dst)
+    if n_nets < 1 or n_nets > L.CA_MAX_NETS or n_res > L.CA_MAX_RESIDUALS:
+        raise ValueError("1..8 ControlNets and at most 16 residuals are supported")
+    if any(len(r) != n_res for r in per_net) or len(scales) != n_nets or any(len(s) != n_res for s in scales):
+        raise ValueError("per_net / scales / dst disagree on the number of residuals")
+    _cuda(*dst, *[t for r in per_net for t in r])
+    res_ptrs = (C.c_void_p * (n_nets * n_res))()
+    sc = (C.c_float * (n_nets * n_res))()
+    dst_ptrs = (C.c_void_p * n_res)()
+    chw = (C.c_int * (3 * n_res))()
+    b_res = b_dst = None
+    dtype = dst[0].dtype
+    for i, d in enumerate(dst):
+        if d.dtype != dtype:
+            raise ValueError("all tensors must share one dtype")
+        if d.dim() == 5:
+            bb, c, f, h, w = d.shape
+            ok = d.is_contiguous() if layout == L.CA_LAYOUT_NCFHW else d.permute(0, 2, 3, 4, 1).is_contiguous()
+        else:
+            n, c, h, w = d.shape
+            bb, f = n // frames, frames
+            ok = layout == L.CA_LAYOUT_BFHWC and d.permute(0, 2, 3, 1).is_contiguous()
+        if not ok or f != frames:
+            raise ValueError(f"dst[{i}] has the wrong layout/frames for layout={layout}")
+        b_dst = bb if b_dst is None else b_dst
+        if bb != b_dst:
+            raise ValueError("dst batch sizes differ")
+        dst_ptrs[i] = d.data_ptr()
+        chw[3 * i], chw[3 * i + 1], chw[3 * i + 2] = c, h, w
+        for k in range(n_nets):
+            r = per_net[k][i]
+            if r.dtype != dtype or r.dim() != 4 or tuple(r.shape[1:]) != (c, h, w) or r.shape[0] % frames:
+                raise ValueError(f"residual [{k}][{i}] must be [(b f), {c}, {h}, {w}] {dtype}, got {tuple(r.shape)} {r.dtype}")
+            ok = r.is_contiguous() if layout == L.CA_LAYOUT_NCFHW else r.permute(0, 2, 3, 1).is_contiguous()
+            if not ok:
+                raise ValueError(f"residual [{k}][{i}] has the wrong memory layout")
+            br = r.shape[0] // frames
+            b_res = br if b_res is None else b_res
+            if br != b_res:
+                raise ValueError("residual batch sizes differ")
+            res_ptrs[k * n_res + i] = r.data_ptr()
+            sc[k * n_res + i] = float(scales[k][i])
+    L.check(L.load().ca_residual_merge(res_ptrs, sc, dst_ptrs, chw, n_nets, n_res, b_res, b_dst, frames, int(add_into_dst),
+                                       layout, _DTYPES[dtype], _stream()), "ca_residual_merge")
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, residual: Optional[torch.Tensor] = None,
+           geglu: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = x @ w^T + bias [-> a*gelu(g)] [+ residual] on tcgen05 tensor cores (ca_linear).
+
+    x [..., k] (dense rows, arbitrary row stride for 2-D views), w [n, k] contiguous (nn.Linear layout), bias [n].
+    """
+    _cuda(x, w, bias, residual)
+    if x.dtype != w.dtype or x.dtype not in (torch.bfloat16, torch.float16):
+        raise ValueError("linear: x and w must both be bf16 or f16")
+    k = x.shape[-1]
+    n = w.shape[0]
+    if w.dim() != 2 or w.shape[1] != k or not w.is_contiguous():
+        raise ValueError("linear: w must be a contiguous [n, k] matrix")
+    lead = x.shape[:-1]
+    x2 = x if x.dim() == 2 else x.reshape(-1, k)
+    if x2.stride(1) != 1:
+        raise ValueError("linear: x rows must be dense")
+    m = x2.shape[0]
+    n_out = n // 2 if geglu else n
+    y = torch.empty((m, n_out), dtype=x.dtype, device=x.device) if out is None else out.reshape(m, n_out)
+    r2 = None
+    if residual is not None:
+        r2 = residual.reshape(m, n_out)
+        if r2.stride(1) != 1 or r2.dtype != x.dtype:
+            raise ValueError("linear: bad residual")
+    b32 = _f32(bias)
+    if b32 is not None and b32.numel() != n:
+        raise ValueError("linear: bias must be [n]")
+    L.check(L.load().ca_linear(x2.data_ptr(), w.data_ptr(), _ptr(b32), _ptr(r2), y.data_ptr(), m, n, k, x2.stride(0),
+                               0 if r2 is None else r2.stride(0), y.stride(0), L.CA_EPI_GEGLU if geglu else L.CA_EPI_NONE,
+                               _dt(x), _stream()), "ca_linear")
+    return y.reshape(*lead, n_out)

@@ -1,0 +1,123 @@
+/*
+ * controlanimate_b200 — C ABI of the B200 (sm_100a) denoising hot path.
+ *
+ * Drop-in boundary for the three operator interfaces of intellerce/controlanimate's denoising
+ * loop.  The reference is pure Python/PyTorch: there is no FFI in it, so each entry
+ * point cites the reference *operator* it replaces (paths relative to the reference repo root).
+ * Host code (controlanimate_b200/*.py) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns ca_status_t (0 = ok) and never throws; ca_last_error() gives the text
+ *   - all pointers are DEVICE pointers unless the parameter is documented as "host"
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no internal synchronisation,
+ *     no device allocation: scratch space is provided by the caller (see *_workspace_bytes)
+ *   - dtype is the storage type of activations; accumulation is always fp32 (or wider)
+ *   - layouts of a video activation with logical shape [b, c, f, h, w]:
+ *       CA_LAYOUT_NCFHW  memory order b,c,f,h,w  (what the reference passes between modules)
+ *       CA_LAYOUT_BFHWC  memory order b,f,h,w,c  (native: "(b f) h w c" = token-major rows of c)
+ */
+#ifndef CONTROLANIMATE_B200_H_
+#define CONTROLANIMATE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { CA_OK = 0, CA_ERR_INVALID = 1, CA_ERR_UNSUPPORTED = 2, CA_ERR_CUDA = 3 } ca_status_t;
+typedef enum { CA_BF16 = 0, CA_F16 = 1, CA_F32 = 2 } ca_dtype_t;
+typedef enum { CA_LAYOUT_NCFHW = 0, CA_LAYOUT_BFHWC = 1 } ca_layout_t;
+
+#define CA_MAX_NETS 8      /* ControlNets per Multi-ControlNet set */
+#define CA_MAX_RESIDUALS 16 /* 12 down + 1 mid for SD1.5 */
+
+/* Library / device introspection. */
+const char* ca_version(void);
+const char* ca_last_error(void);
+/* 10*major+minor of the current device (100 on B200); negative on error. */
+int ca_device_sm(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel (2): y = SiLU(GroupNorm(x + temb[b, c])).
+ * Replaces InflatedGroupNorm.forward + F.silu (animatediff/models/resnet.py:23-31, 191-192,
+ * 199-208) and conv_norm_out + conv_act (animatediff/models/unet.py:614-615); with apply_silu = 0
+ * also the transformer-entry GroupNorms (motion_module.py:144, attention.py:131).
+ *   x, y      [b,c,f,h,w] in `layout`, dtype `dtype`; y may alias x
+ *   gamma,beta[c] fp32;  temb [b,c] fp32 or NULL (the projected time embedding, resnet.py:196-200)
+ *   per_frame 1: statistics per (b, f, group) over (c/groups, h, w)  (use_inflated_groupnorm, v2)
+ *             0: statistics per (b, group) over (c/groups, f, h, w)  (plain nn.GroupNorm, v1)
+ *   workspace ca_groupnorm_workspace_bytes(...) bytes of scratch (may be NULL if that is 0)
+ * ------------------------------------------------------------------------------------------- */
+size_t ca_groupnorm_workspace_bytes(int b, int c, int f, int h, int w, int groups, int per_frame, int layout,
+                                    int dtype);
+int ca_groupnorm_silu(const void* x, void* y, const float* gamma, const float* beta, const float* temb, int b, int c,
+                      int f, int h, int w, int groups, float eps, int per_frame, int apply_silu, int layout,
+                      int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel (3): single-pass Multi-ControlNet residual merge.
+ *   dst_i  (=|+=)  sum_k scales[k*n_res + i] * res[k*n_res + i]        for i in [0, n_res)
+ * Replaces the per-net conditioning-scale multiply and the sum over nets (diffusers 0.23.0
+ * ControlNetModel/MultiControlNetModel.forward, called at modules/controlresiduals_pipeline.py:
+ * 294-302), the 13 '(b f) c h w -> b c f h w' rearranges (:304-312) and, with add_into_dst = 1,
+ * the skip additions animatediff/models/unet.py:567-576, 584-585.
+ *   res     host array [n_nets*n_res] of device pointers, each a residual of shape
+ *           [(b_res f), c_i, h_i, w_i]: NCHW per frame when layout == CA_LAYOUT_NCFHW (what
+ *           diffusers ControlNets emit), or [(b_res f), h_i, w_i, c_i] when CA_LAYOUT_BFHWC
+ *   scales  host array [n_nets*n_res] fp32 (guess-mode logspace factors folded in by the caller)
+ *   dst     host array [n_res] of device pointers: [b_dst, c_i, f, h_i, w_i] in `layout`
+ *   chw     host array [n_res*3] = c_i, h_i, w_i
+ *   b_res   1 or b_dst (batch broadcast, unet.py:572 in guess mode + CFG)
+ *   add_into_dst  0: dst = sum (contract-preserving producer);  1: dst += sum (in-place on skips)
+ * ------------------------------------------------------------------------------------------- */
+int ca_residual_merge(const void* const* res, const float* scales, void* const* dst, const int* chw, int n_nets,
+                      int n_res, int b_res, int b_dst, int f, int add_into_dst, int layout, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel (1) pieces, all on token-major activations: row t = (b*f + frame)*d + site, d = h*w.
+ * ------------------------------------------------------------------------------------------- */
+
+/* y[t,:] = LayerNorm(x[t,:]) * gamma + beta (+ pe[frame(t), :]).
+ * Replaces nn.LayerNorm (motion_module.py:214, 221) and, with pe != NULL, the positional-encoding
+ * add of VersatileAttention.forward (motion_module.py:285-288, PositionalEncoding :227-245), done
+ * in token order so the '(b f) d c -> (b d) f c' rearrange never materialises.
+ *   x,y [rows, c] dtype; gamma,beta [c] fp32; pe [>=f, c] fp32 or NULL; rows = b*f*d  */
+int ca_layernorm_pe(const void* x, void* y, const float* gamma, const float* beta, const float* pe, long long rows,
+                    int c, int f, int d, float eps, int dtype, void* stream);
+
+/* Temporal self-attention core: for every (b, site, head): O = softmax(Q K^T * scale) V over the
+ * f frames.  Replaces the head split + attention + head merge of the AttentionProcessor
+ * (modules/attention_processor.py:56-62 / :247-256; xformers memory_efficient_attention on the
+ * reference's default GPU path) for VersatileAttention's temporal mode (motion_module.py:285,321,327).
+ *   q,k,v  token-major [b*f*d, *] with row strides ldq/ldk/ldv (elements); head hh occupies
+ *          columns [hh*head_dim, (hh+1)*head_dim).  A packed [T, 3C] QKV buffer is passed as
+ *          q = base, k = base + C, v = base + 2C, ld* = 3C.
+ *   o      [b*f*d, heads*head_dim] with row stride ldo
+ *   seq_major 0: rows are token-major, t = (b*f + frame)*d + site (native layout)
+ *             1: rows are the reference's "(b d) f c" order, t = (b*d + site)*f + frame — exactly the
+ *                hidden_states an AttentionProcessor receives from VersatileAttention (boundary B1)
+ *   constraints: f <= 32, head_dim % 8 == 0, head_dim <= 256, dtype bf16/f16, 16-byte aligned rows */
+int ca_temporal_attn_core(const void* q, const void* k, const void* v, void* o, int b, int f, int d, int heads,
+                          int head_dim, long long ldq, long long ldk, long long ldv, long long ldo, int seq_major,
+                          float scale, int dtype, void* stream);
+
+/* Dense projection on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA operands):
+ *   y = epilogue(x @ w^T + bias) (+ residual)
+ * Replaces the nn.Linear projections of the motion module: to_q/to_k/to_v (fused as one [3C, C]
+ * weight), to_out[0] (+bias, +residual: motion_module.py:215-219), proj_in/proj_out (:147, :155),
+ * GEGLU ff.net.0.proj and ff.net.2 (:221).
+ *   x [m, k] row stride ldx; w [n, k] row-major (nn.Linear layout); bias [n] fp32 or NULL;
+ *   residual [m, n_out] row stride ldr or NULL; y [m, n_out] row stride ldy
+ *   epilogue: CA_EPI_NONE n_out = n;  CA_EPI_GEGLU n_out = n/2: y = a * gelu_erf(g) where a/g are
+ *   columns j and j + n/2 of the product (diffusers GEGLU chunk(2, -1))
+ *   constraints: k % 16 == 0, n % 16 == 0, dtype bf16/f16 */
+typedef enum { CA_EPI_NONE = 0, CA_EPI_GEGLU = 1 } ca_epilogue_t;
+int ca_linear(const void* x, const void* w, const float* bias, const void* residual, void* y, long long m, int n,
+              int k, long long ldx, long long ldr, long long ldy, int epilogue, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONTROLANIMATE_B200_H_ */

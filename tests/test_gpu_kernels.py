@@ -1,0 +1,243 @@
+"""GPU parity tests: every CUDA kernel, called through the C ABI (ctypes), against the CPU oracle
+(oracle/ref_ops.py, itself pinned to the reference's own Python by tests/test_oracle_golden.py).
+
+Tolerances (BASELINE.json north_star): per-op max relative error <= 2e-3 for bf16 storage with fp32
+accumulation.  `ref` is the oracle evaluated in fp32 on the SAME (bf16-rounded) inputs and the error is
+max(|y - ref| - q(ref)) / max|ref|, where q(ref) = half an ulp of the storage type at |ref| is the
+unavoidable quantisation of writing the result as bf16/f16 (bf16 keeps 8 significant bits, so storing
+alone costs up to 2^-8 = 3.9e-3 relative; the 2e-3 budget is for the arithmetic).  fp32 storage has
+q = 0 and is held to 2e-5, which pins the arithmetic itself.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_ops as R
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+REL = {torch.bfloat16: 2e-3, torch.float16: 1e-3, torch.float32: 2e-5}
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device")
+    from controlanimate_b200 import _lib, ops as O
+    lib = _lib.load(build_if_missing=False)
+    assert lib.ca_device_sm() == 100, "these kernels are built for sm_100a (B200) only"
+    return O
+
+
+MANT = {torch.bfloat16: 8, torch.float16: 11}
+
+
+def relerr(y, ref):
+    dt = y.dtype
+    y = y.detach().float().cpu()
+    assert torch.isfinite(y).all()
+    err = (y - ref).abs()
+    if dt in MANT:  # half an ulp of the storage type at |ref|
+        expo = torch.floor(torch.log2(ref.abs().clamp_min(1e-30)))
+        err = (err - 0.5 * torch.pow(2.0, expo - (MANT[dt] - 1)) * 1.0001).clamp_min(0)
+    return float(err.max() / ref.abs().max().clamp_min(1e-12))
+
+
+def to_layout(x, layout):
+    """Return a [b,c,f,h,w] CUDA tensor with the requested memory layout."""
+    x = x.cuda()
+    if layout == "ncfhw":
+        return x.contiguous()
+    return x.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
+
+
+GN_CASES = [
+    # b, c, f, h, w, groups, per_frame, temb
+    (2, 64, 3, 6, 5, 32, True, True),      # ragged h*w -> scalar path in NCFHW
+    (2, 64, 3, 8, 4, 8, True, False),
+    (1, 320, 4, 16, 16, 32, True, True),   # cpg = 10 (vectors straddle groups in BFHWC)
+    (2, 96, 2, 8, 8, 32, False, True),     # v1 (non-inflated) statistics over frames too
+    (1, 640, 2, 64, 64, 32, True, True),   # 160 KB groups -> multi-chunk domains + domain barrier
+    (1, 32, 16, 64, 64, 32, False, False), # one channel per group, long domains (split launch path)
+    (2, 1280, 2, 8, 8, 32, True, True),    # tiny groups
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32, torch.float16])
+@pytest.mark.parametrize("layout", ["ncfhw", "bfhwc"])
+@pytest.mark.parametrize("case", GN_CASES)
+def test_groupnorm_silu(ops, case, layout, dtype):
+    b, c, f, h, w, groups, per_frame, use_temb = case
+    x = (synth.tensor(7, f"gn.{case}", (b, c, f, h, w)) * 1.5 + 0.4).to(dtype)
+    gamma = 1 + synth.tensor(7, "gn.gamma", (c,), 0.1)
+    beta = synth.tensor(7, "gn.beta", (c,), 0.1)
+    temb = synth.tensor(7, "gn.temb", (b, c)) if use_temb else None
+    for silu in (True, False):
+        ref = R.groupnorm_silu(x.float(), gamma, beta, groups, 1e-5, per_frame, temb, silu)
+        y = ops.groupnorm_silu(to_layout(x, layout), gamma.cuda(), beta.cuda(), groups, 1e-5, per_frame=per_frame, silu=silu,
+                               temb=None if temb is None else temb.cuda())
+        assert y.shape == x.shape
+        assert relerr(y, ref) <= REL[dtype], (case, layout, dtype, silu)
+
+
+def test_groupnorm_in_place_and_errors(ops):
+    x = synth.tensor(3, "gn.ip", (1, 64, 2, 8, 8)).cuda().bfloat16()
+    g, b = torch.ones(64, device="cuda"), torch.zeros(64, device="cuda")
+    ref = R.groupnorm_silu(x.float().cpu(), g.cpu(), b.cpu(), 32, 1e-5)
+    y = ops.groupnorm_silu(x, g, b, 32, 1e-5, out=x)
+    assert y.data_ptr() == x.data_ptr() and relerr(y, ref) <= 2e-3
+    with pytest.raises(ValueError):
+        ops.groupnorm_silu(x, g, b, 7, 1e-5)                      # c not divisible by groups
+    with pytest.raises(ValueError):
+        ops.groupnorm_silu(x.cpu(), g, b, 32, 1e-5)               # no CPU fallback
+    with pytest.raises(ValueError):
+        ops.groupnorm_silu(x[:, :, :, ::2], g, b, 32, 1e-5)       # strided view
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("c,f,d,b", [(320, 16, 12, 2), (64, 5, 7, 1), (1280, 8, 3, 2), (640, 32, 4, 1)])
+def test_layernorm_pe(ops, c, f, d, b, dtype):
+    x = (synth.tensor(5, f"ln.{c}.{f}", (b * f, d, c)) * 2 + 0.3).to(dtype)
+    gamma = 1 + synth.tensor(5, "ln.g", (c,), 0.1)
+    beta = synth.tensor(5, "ln.b", (c,), 0.1)
+    pe = R.positional_encoding(32, c)
+    ref = torch.nn.functional.layer_norm(x.float(), (c,), gamma, beta, 1e-5)
+    y = ops.layernorm_pe(x.cuda(), gamma.cuda(), beta.cuda(), 1e-5)
+    assert relerr(y, ref) <= REL[dtype]
+    # + PE in token order == the reference's "(b f) d c -> (b d) f c ; + pe[:, :f]" (motion_module.py:285-288)
+    ref_pe = (ref.reshape(b, f, d, c) + pe[0, :f][None, :, None, :]).reshape(b * f, d, c)
+    y = ops.layernorm_pe(x.cuda(), gamma.cuda(), beta.cuda(), 1e-5, pe=pe.cuda(), frames=f, sites=d)
+    assert relerr(y, ref_pe) <= REL[dtype]
+
+
+ATTN_CASES = [
+    # b, f, d, heads, hd
+    (2, 16, 40, 8, 40),    # SD1.5 level 0 head_dim (k8 tail step)
+    (1, 16, 24, 8, 80),
+    (1, 16, 9, 8, 160),    # d not a multiple of the site tile
+    (2, 8, 33, 8, 40),     # config-1 frame count
+    (1, 32, 10, 8, 40),    # PE max_len (two query m-tiles)
+    (1, 24, 5, 8, 80),     # v1 max_len
+    (2, 5, 7, 8, 8),       # tiny golden-shaped case (f not a multiple of 8)
+    (1, 12, 6, 4, 16),
+    (1, 1, 3, 2, 8),       # single frame: softmax over one key
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("case", ATTN_CASES)
+def test_temporal_attention_core(ops, case, dtype):
+    b, f, d, heads, hd = case
+    C = heads * hd
+    T = b * f * d
+    qkv = synth.tensor(11, f"attn.{case}", (T, 3 * C)).to(dtype)
+    q, k, v = (qkv[:, i * C:(i + 1) * C].float() for i in range(3))
+
+    def seq(t):  # token-major [(b f d), C] -> [(b d), f, C]
+        return t.reshape(b, f, d, C).permute(0, 2, 1, 3).reshape(b * d, f, C)
+
+    ref = R.attention_core(seq(q), seq(k), seq(v), heads).reshape(b, d, f, C).permute(0, 2, 1, 3).reshape(T, C)
+    g = qkv.cuda()
+    o = ops.temporal_attention_core(g[:, :C], g[:, C:2 * C], g[:, 2 * C:], batch=b, frames=f, sites=d, heads=heads)
+    assert relerr(o, ref) <= REL[dtype], case
+    # separate (unpacked) buffers take the same path with ld = C
+    o2 = ops.temporal_attention_core(g[:, :C].contiguous(), g[:, C:2 * C].contiguous(), g[:, 2 * C:].contiguous(),
+                                     batch=b, frames=f, sites=d, heads=heads)
+    assert torch.equal(o, o2)
+
+
+def test_temporal_attention_rejects_long_sequences(ops):
+    q = torch.zeros(33 * 2, 64, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        ops.temporal_attention_core(q, q, q, batch=1, frames=33, sites=2, heads=8)
+
+
+def _residual_sets(seed, n_nets, b, f, hw0, dtype, chans=(32, 64, 128, 128)):
+    shapes = synth.residual_shapes(chans)
+    sets = []
+    for k in range(n_nets):
+        cur = []
+        for i, (c, div) in enumerate(shapes):
+            s = max(hw0 // div, 1)
+            cur.append(synth.tensor(seed, f"res.{k}.{i}", (b * f, c, s, s + (1 if i % 2 else 0))).to(dtype))
+        sets.append(cur)
+    return sets
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("n_nets,b_res,b_dst,guess", [(1, 2, 2, False), (2, 2, 2, False), (4, 1, 2, True), (5, 1, 1, False)])
+def test_residual_merge_reference_layout(ops, n_nets, b_res, b_dst, guess, dtype):
+    """B3 contract in the reference's layouts: (b f) c h w per net -> b c f h w, optionally += into skips."""
+    from controlanimate_b200 import _lib as L
+    f = 3
+    sets = _residual_sets(21, n_nets, b_res, f, 8, dtype)
+    cond = [1.0, 0.5, 0.35, 0.4, 0.8][:n_nets]
+    level = torch.logspace(-1, 0, 13) if guess else torch.ones(13)
+    scales = [[float(level[i]) * cond[k] for i in range(13)] for k in range(n_nets)]
+    down_ref, mid_ref = R.merge_controlnet_residuals([[t.float() for t in s] for s in sets], cond, f, guess_mode=guess)
+    ref = list(down_ref) + [mid_ref]
+    # producer mode (dst = sum)
+    dst = [torch.empty((b_res, r.shape[1], f, r.shape[3], r.shape[4]), dtype=dtype, device="cuda") for r in ref]
+    ops.residual_merge([[t.cuda() for t in s] for s in sets], scales, dst, frames=f, add_into_dst=False, layout=L.CA_LAYOUT_NCFHW)
+    for d, r in zip(dst, ref):
+        assert relerr(d, r) <= REL[dtype]
+    # in-place mode on skips with batch broadcast (unet.py:567-585)
+    skips = [synth.tensor(22, f"skip.{i}", (b_dst, r.shape[1], f, r.shape[3], r.shape[4])).to(dtype) for i, r in enumerate(ref)]
+    want = [s.float() + r for s, r in zip(skips, ref)]
+    got = [s.cuda() for s in skips]
+    ops.residual_merge([[t.cuda() for t in s] for s in sets], scales, got, frames=f, add_into_dst=True, layout=L.CA_LAYOUT_NCFHW)
+    for g, wv in zip(got, want):
+        assert relerr(g, wv) <= REL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_residual_merge_native_layout(ops, dtype):
+    from controlanimate_b200 import _lib as L
+    f, b = 4, 2
+    sets = _residual_sets(23, 2, b, f, 8, dtype)
+    scales = [[1.0] * 13, [0.5] * 13]
+    ref = [a.float() + 0.5 * c.float() for a, c in zip(*sets)]
+    cl = [[t.cuda().contiguous(memory_format=torch.channels_last) for t in s] for s in sets]
+    skips = [synth.tensor(24, f"skipn.{i}", tuple(r.shape)).to(dtype) for i, r in enumerate(ref)]
+    got = [s.cuda().contiguous(memory_format=torch.channels_last) for s in skips]
+    ops.residual_merge(cl, scales, got, frames=f, add_into_dst=True, layout=L.CA_LAYOUT_BFHWC)
+    for g, s, r in zip(got, skips, ref):
+        assert relerr(g, s.float() + r) <= REL[dtype]
+
+
+LINEAR_CASES = [
+    # m, n, k
+    (256, 64, 64), (128, 320, 320), (1000, 960, 320), (4096, 640, 640), (2048, 1280, 2560), (77, 192, 128), (300, 2560, 320),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("m,n,k", LINEAR_CASES)
+def test_linear_tcgen05(ops, m, n, k, dtype):
+    """nn.Linear semantics (motion_module.py:147,155 and the processor's to_q/k/v/to_out) on tcgen05."""
+    x = synth.tensor(31, f"lin.x.{m}.{k}", (m, k)).to(dtype)
+    w = synth.tensor(31, f"lin.w.{n}.{k}", (n, k), k ** -0.5).to(dtype)
+    bias = synth.tensor(31, "lin.b", (n,), 0.1)
+    res = synth.tensor(31, f"lin.r.{m}.{n}", (m, n)).to(dtype)
+    ref = torch.nn.functional.linear(x.float(), w.float(), bias)
+    y = ops.linear(x.cuda(), w.cuda(), bias.cuda())
+    assert relerr(y, ref) <= REL[dtype]
+    y = ops.linear(x.cuda(), w.cuda(), None, residual=res.cuda())
+    assert relerr(y, torch.nn.functional.linear(x.float(), w.float()) + res.float()) <= REL[dtype]
+    if n % 32 == 0:
+        a, g = ref.chunk(2, dim=-1)
+        y = ops.linear(x.cuda(), w.cuda(), bias.cuda(), geglu=True)
+        assert y.shape == (m, n // 2)
+        assert relerr(y, a * torch.nn.functional.gelu(g)) <= REL[dtype]
+
+
+def test_linear_strided_input_and_repeat(ops):
+    """x may be a column slice of a wider buffer (row stride > k); repeated launches reuse barriers/TMEM cleanly."""
+    buf = synth.tensor(32, "lin.buf", (512, 3 * 128)).bfloat16().cuda()
+    w = synth.tensor(32, "lin.w2", (256, 128), 128 ** -0.5).bfloat16().cuda()
+    for i in range(3):
+        xs = buf[:, i * 128:(i + 1) * 128]
+        y = ops.linear(xs, w)
+        ref = torch.nn.functional.linear(xs.float().cpu(), w.float().cpu())
+        assert relerr(y, ref) <= 2e-3
