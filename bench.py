@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Headline benchmark: denoised frames/s of the ControlAnimate hot loop on B200 (BASELINE.json configs[1]).
+
+Workload (config 2): SD1.5 UNet3D + mm_sd_v15_v2 motion modules + 2 ControlNets, 16 frames 512x512 (latent 64x64),
+CFG 7.5 (b=2), DDIM 20 steps, bf16 storage / fp32 accumulate, random-init weights, synthetic latents / prompt
+embeddings / control images.  One bench "step" = ONE denoising step of the loop (ControlNets -> residual merge ->
+UNet3D -> CFG -> DDIM, reference controlanimation_pipeline.py:793-849); frames/s = frames / (20 * step time).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this framework (sm_100a kernels)
+  python bench.py --impl reference ...                           # CPU arm: the oracle restatement of the reference's
+                                                                 # own PyTorch path on the host cores (bounded sample)
+N > 1 (torchrun): every rank denoises its own 16-frame window of one long clip (windows overlap by 4 latent frames,
+exchanged and blended each step with NCCL send/recv) -> weak scaling, value = N * 16 / (20 * step time).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DDIM_STEPS = 20
+FRAMES = 16
+LATENT = 64
+GUIDANCE = 7.5
+COND_SCALE = [1.0, 0.5]
+OVERLAP = 4
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]), tf_sustained=float(d["bf16_tflops_sustained"]),
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(int(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle (CPU restatement of the reference's PyTorch path)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step_factory(frames_sample: int, latent: int, n_nets: int = 2, seed: int = 0):
+    """Return (step_fn, description).  One denoising step of config 2 restricted to `frames_sample` frames at full
+    resolution: frames are independent everywhere except the (tiny) temporal attention, so frames/step-second of the
+    sample is the per-frame throughput of the full 16-frame step."""
+    from oracle import ref_ops as R
+    from oracle import ref_unet3d as U
+    from oracle import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = synth.unet_config(tiny=False)
+    gen = torch.Generator().manual_seed(seed)
+
+    def fill(shapes):
+        sd = {}
+        for k, shp in shapes.items():
+            if k.endswith(".pe"):
+                sd[k] = R.positional_encoding(shp[1], shp[2])
+            elif len(shp) >= 2:
+                fan_in = 1
+                for s in shp[1:]:
+                    fan_in *= s
+                sd[k] = torch.randn(shp, generator=gen) * fan_in ** -0.5
+            elif k.endswith("weight") and "norm" in k:
+                sd[k] = 1 + 0.1 * torch.randn(shp, generator=gen)
+            else:
+                sd[k] = 0.1 * torch.randn(shp, generator=gen)
+        return sd
+
+    sd_u = fill(U.unet3d_shapes(cfg))
+    sd_c = [fill(U.controlnet_shapes(cfg)) for _ in range(n_nets)]
+    f = frames_sample
+    latents = torch.randn(1, 4, f, latent, latent, generator=gen)
+    prompt = torch.randn(2, 77, 768, generator=gen)
+    images = [torch.randn(2 * f, 3, latent * 8, latent * 8, generator=gen) for _ in range(n_nets)]
+    acp = R.ddim_alphas_cumprod()
+    t = R.ddim_timesteps(DDIM_STEPS)[0]
+    state = {"latents": latents}
+
+    @torch.no_grad()
+    def step():
+        lat = state["latents"]
+        model_in = torch.cat([lat] * 2)
+        x2d = model_in.permute(0, 2, 1, 3, 4).reshape(2 * f, 4, latent, latent)
+        ctx = torch.cat([prompt] * f)
+        per_net = [U.controlnet_forward(sd_c[k], cfg, x2d, t, ctx, images[k]) for k in range(n_nets)]
+        down, mid = R.merge_controlnet_residuals(per_net, COND_SCALE[:n_nets], f)
+        noise = U.unet3d_forward(sd_u, cfg, model_in, t, prompt, down, mid)
+        state["latents"] = R.ddim_step(R.cfg_combine(noise, GUIDANCE), t, lat, acp, DDIM_STEPS)
+
+    desc = (f"oracle (torch fp32 CPU restatement of the reference path), one denoising step of config 2 on {f} of {FRAMES} frames "
+            f"at full 512x512 (latent {latent}x{latent}), b=2 CFG, {n_nets} ControlNets; frames/s = {f}/(20*step_s)")
+    return step, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    f = args.cpu_frames
+    step, desc = cpu_reference_step_factory(f, args.latent)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = f / (DDIM_STEPS * dt)
+    line = {
+        "impl": "reference", "metric": "denoised frames/s", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, parallelism="cpu"),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, parallelism):
+    return {"workload": f"SD1.5 UNet3D + mm_sd_v15_v2 motion modules + 2 ControlNets, {FRAMES} frames 512x512 (latent "
+                        f"{args.latent}x{args.latent}), CFG {GUIDANCE} (b=2), DDIM {DDIM_STEPS} steps; one bench step = one denoising step",
+            "frames_per_window": FRAMES, "ddim_steps": DDIM_STEPS, "controlnets": 2, "cond_scale": COND_SCALE,
+            "parallelism": parallelism, "window_overlap_frames": OVERLAP,
+            "l2": "per-step working set (>10 GB of activations and 4 GB of weights) exceeds the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from controlanimate_b200 import _lib, ops, parallel, pipeline, profiler, unet as un, utils
+    from oracle import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load(build_if_missing=False)
+    if lib.ca_device_sm() != 100:
+        raise SystemExit(f"sm_{lib.ca_device_sm()} device: these kernels are sm_100a only")
+    torch.backends.cudnn.benchmark = True
+
+    cfg = synth.unet_config(tiny=False)
+    dtype = torch.bfloat16
+    unet = utils.build_on_device(lambda: un.UNet3DConditionModel(**cfg), dev, dtype, seed=1)
+    nets = [utils.build_on_device(lambda: un.ControlNetModel(), dev, dtype, seed=2 + k) for k in range(2)]
+    mc = pipeline.MultiControlNetResiduals(nets, COND_SCALE)
+    sched = pipeline.DDIMScheduler()
+    timesteps = sched.set_timesteps(DDIM_STEPS)
+    loop = pipeline.DenoisingLoop(unet, mc, sched, guidance_scale=GUIDANCE)
+    windows = parallel.WindowParallel(rank, world, FRAMES, OVERLAP) if world > 1 else None
+
+    f, lat = FRAMES, args.latent
+    g = torch.Generator(device="cpu").manual_seed(100 + rank)
+    # host-side inputs (pinned): what a caller of the public API holds
+    h_latents = torch.randn(1, 4, f, lat, lat, generator=g).pin_memory()
+    h_prompt = torch.randn(2, 77, 768, generator=g).to(dtype).pin_memory()
+    h_images = [torch.randn(2 * f, 3, lat * 8, lat * 8, generator=g).to(dtype) for _ in range(2)]
+    mc.prep_images = [im.to(dev) for im in h_images]          # prepared once per window (prep_control_images)
+    d_prompt = h_prompt.to(dev)
+    h_out = torch.empty_like(h_latents).pin_memory()
+
+    def one_step(latents, i):
+        t = timesteps[i % DDIM_STEPS]
+        latents = loop.step(latents, t, d_prompt)
+        if windows is not None:
+            latents = windows.exchange(latents)
+        return latents
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident run (value) -------------------------------------------------------------------------
+    latents = h_latents.to(dev)
+    for i in range(args.warmup):
+        latents = one_step(latents, i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    profiler.reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        latents = one_step(latents, i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = profiler.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end through the public API with HOST buffers (e2e) ----------------------------------------------
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        d_lat = h_latents.to(dev, non_blocking=True)
+        d_p = h_prompt.to(dev, non_blocking=True)
+        out = loop.step(d_lat, timesteps[i % DDIM_STEPS], d_p)
+        if windows is not None:
+            out = windows.exchange(out)
+        h_out.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller consumes the latents on the host
+        h_latents.copy_(h_out)
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3) / args.steps
+
+    # max over ranks
+    if world > 1:
+        tms = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(tms[0]), float(tms[1])
+
+    # ---- per-kernel timing pass (CUDA events around every C-ABI launch, on the launching stream) ---------------
+    kern = None
+    if rank == 0:
+        profiler.enable(True)
+        lat2 = latents
+        for i in range(2):
+            lat2 = loop.step(lat2, timesteps[i], d_prompt)
+        torch.cuda.synchronize()
+        kern = profiler.summary(measured_peaks())
+        profiler.enable(False)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        value = world * f / (DDIM_STEPS * ms * 1e-3)
+        e2e = world * f / (DDIM_STEPS * ms_e2e * 1e-3)
+        top = kern["dominant"]
+        line = {
+            "metric": "denoised frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, parallelism="single" if world == 1 else f"frame-windows x{world} (overlap {OVERLAP})"),
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h_latents.numel() * 4 + h_prompt.numel() * 2, "d2h_bytes_per_step": h_out.numel() * 4},
+            "gpu_launches": launches,
+            "roofline": top,
+            "kernels": kern["families"],
+            "own_kernel_share_of_step": kern["own_share"],
+            "peaks": peaks,
+        }
+        if args.cpu_baseline:
+            step, desc = cpu_reference_step_factory(args.cpu_frames, args.latent)
+            step()
+            t0 = time.perf_counter()
+            step()
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": args.cpu_frames / (DDIM_STEPS * dt), "unit": "frames/s", "cores": torch.get_num_threads(),
+                                    "kind": "port", "sample": desc, "ms_per_step": dt * 1e3}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--latent", type=int, default=LATENT)
+    ap.add_argument("--cpu-frames", type=int, default=1, help="frames of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

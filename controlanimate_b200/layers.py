@@ -1,0 +1,441 @@
+"""Host-side mirror of the reference's operator surface for the denoising hot path.
+
+Every class keeps the reference module's name-space (state_dict keys, forward signature) and routes
+the arithmetic to the sm_100a kernels behind the C ABI (controlanimate_b200.ops).  Nothing here has
+a CPU or eager fallback: tensors must be CUDA bf16/f16 and the library must load.
+
+Native activation layout: a video activation with logical shape [b, c, f, h, w] is stored in
+memory order b,f,h,w,c ("BFHWC").  Its 4-D view [(b f), c, h, w] is torch `channels_last` (what
+cuDNN wants for 16-bit convolutions) and its 2-D view [(b f h w), c] is the token matrix that the
+transformer kernels and tcgen05 GEMMs consume — so none of the reference's einops rearrange copies
+(resnet.py:16-18,27-29; motion_module.py:139,146,155-159,285,327; attention.py:124,137,153-164) exist.
+Modules also accept the reference's NCFHW-contiguous tensors at their public `forward` (drop-in
+boundaries B2/B4) and return the layout they were given.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import ops
+
+
+# --------------------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------------------
+def f32(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """fp32 copy of a (small) parameter, cached on the tensor and refreshed when it is modified in place
+    or moved: kernels read gamma/beta/bias/pe as fp32 while the module may be held in bf16 (`.half()` in the
+    reference, modules/controlanimate_pipeline.py:108-110)."""
+    if p is None:
+        return None
+    if p.dtype == torch.float32 and p.is_contiguous():
+        return p.detach()
+    key = (p._version, p.data_ptr(), p.device)
+    cached = getattr(p, "_ca_f32", None)
+    if cached is None or cached[0] != key:
+        cached = (key, p.detach().float().contiguous())
+        try:
+            p._ca_f32 = cached
+        except AttributeError:  # pragma: no cover
+            pass
+    return cached[1]
+
+
+def to_native(x: torch.Tensor) -> torch.Tensor:
+    """[b,c,f,h,w] (any dense layout) -> same logical tensor with BFHWC memory order (copy only if needed)."""
+    if ops.video_layout(x) == L.CA_LAYOUT_BFHWC:
+        return x
+    return x.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
+
+
+def frames4(x5: torch.Tensor) -> torch.Tensor:
+    """BFHWC [b,c,f,h,w] -> channels_last [(b f), c, h, w] view."""
+    b, c, f, h, w = x5.shape
+    return x5.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
+
+
+def video5(x4: torch.Tensor, frames: int) -> torch.Tensor:
+    """channels_last [(b f), c, h, w] -> BFHWC [b,c,f,h,w] view."""
+    n, c, h, w = x4.shape
+    return x4.reshape(n // frames, frames, c, h, w).permute(0, 2, 1, 3, 4)
+
+
+def tokens(x4: torch.Tensor) -> torch.Tensor:
+    """channels_last [(b f), c, h, w] -> token matrix [(b f h w), c] view."""
+    n, c, h, w = x4.shape
+    return x4.permute(0, 2, 3, 1).reshape(n * h * w, c)
+
+
+def from_tokens(t: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
+    return t.reshape(n, h, w, t.shape[-1]).permute(0, 3, 1, 2)
+
+
+def _cl(x4: torch.Tensor) -> torch.Tensor:
+    return x4 if x4.is_contiguous(memory_format=torch.channels_last) else x4.contiguous(memory_format=torch.channels_last)
+
+
+def group_norm(x4: torch.Tensor, norm: nn.GroupNorm, frames: int, *, per_frame: bool = True, silu: bool = False,
+               temb: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Kernel (2) on a native 4-D activation; returns a channels_last 4-D tensor."""
+    y5 = ops.groupnorm_silu(video5(_cl(x4), frames), f32(norm.weight), f32(norm.bias), norm.num_groups, norm.eps,
+                            per_frame=per_frame, silu=silu, temb=temb)
+    return frames4(y5)
+
+
+class _FusedWeights:
+    """Concatenated projection weights (to_q|to_k|to_v -> one [3C, C] GEMM), rebuilt if a source changes."""
+
+    def __init__(self):
+        self._key = None
+        self._w = None
+
+    def get(self, *ws: torch.Tensor) -> torch.Tensor:
+        key = tuple((w._version, w.data_ptr(), w.dtype) for w in ws)
+        if key != self._key:
+            self._w = torch.cat([w.detach() for w in ws], dim=0).contiguous()
+            self._key = key
+        return self._w
+
+
+# --------------------------------------------------------------------------------------------------
+# B1: AttentionProcessor for VersatileAttention (temporal self-attention)
+# --------------------------------------------------------------------------------------------------
+class B200TemporalAttnProcessor(nn.Module):
+    """Drop-in AttentionProcessor (reference modules/attention_processor.py:186-272 is the semantic spec).
+
+    `processor(attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None)` with
+    hidden_states [(b d), f, C] already LayerNorm'd and PE-added by VersatileAttention.forward
+    (motion_module.py:285-288,321).  Computes to_out(softmax(q k^T scale) v) with: one fused tcgen05
+    GEMM for to_q|to_k|to_v, the TMA/mma temporal-attention core reading the "(b d) f c" row order in
+    place, and a tcgen05 GEMM with fused bias for to_out[0].  nn.Module so it can live in the
+    ModuleList IP-Adapter builds (modules/ip_adapter.py:184).
+    """
+
+    def __init__(self, hidden_size=None, cross_attention_dim=None):
+        super().__init__()
+        self._qkv = _FusedWeights()
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
+        if encoder_hidden_states is not None or attention_mask is not None:
+            raise ValueError("B200TemporalAttnProcessor handles temporal SELF-attention without a mask only")
+        for name in ("spatial_norm", "group_norm", "norm_cross"):
+            if getattr(attn, name, None) is not None:
+                raise ValueError(f"attn.{name} is not supported on the temporal path")
+        if getattr(attn, "residual_connection", False) or getattr(attn, "rescale_output_factor", 1.0) != 1.0:
+            raise ValueError("residual_connection / rescale_output_factor are not supported on the temporal path")
+        if hidden_states.dim() != 3:
+            raise ValueError("expected hidden_states [(b d), f, C]")
+        if attn.to_q.bias is not None:
+            raise ValueError("temporal attention projections carry no bias (attention_bias=False)")
+        bd, f, c = hidden_states.shape
+        x = hidden_states.contiguous().reshape(bd * f, c)
+        wqkv = self._qkv.get(attn.to_q.weight, attn.to_k.weight, attn.to_v.weight)
+        qkv = ops.linear(x, wqkv)
+        o = ops.temporal_attention_core(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], batch=1, frames=f, sites=bd,
+                                        heads=attn.heads, scale=attn.scale, seq_major=True)
+        out = ops.linear(o, attn.to_out[0].weight, f32(attn.to_out[0].bias))
+        return out.reshape(bd, f, c)  # to_out[1] is Dropout(0) in eval
+
+
+# --------------------------------------------------------------------------------------------------
+# B2: motion module
+# --------------------------------------------------------------------------------------------------
+class _PositionalEncoding(nn.Module):
+    """Holds the `pe` buffer of reference PositionalEncoding (motion_module.py:227-245)."""
+
+    def __init__(self, d_model: int, max_len: int):
+        super().__init__()
+        position = torch.arange(max_len).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+        pe = torch.zeros(1, max_len, d_model)
+        pe[0, :, 0::2] = torch.sin(position * div_term)
+        pe[0, :, 1::2] = torch.cos(position * div_term)
+        self.register_buffer("pe", pe)
+
+    def _apply(self, fn, recurse=True):
+        # follow device moves but keep the table in fp32 (the kernel adds it in fp32; `.half()`/`.bfloat16()` on the
+        # model must not quantise it)
+        pe = self.pe
+        super()._apply(fn, recurse)
+        self.pe = pe.to(device=self.pe.device, dtype=torch.float32)
+        return self
+
+
+class TemporalAttention(nn.Module):
+    """Parameter container mirroring VersatileAttention (motion_module.py:248-270) incl. the processor protocol."""
+
+    def __init__(self, dim: int, heads: int, max_len: Optional[int]):
+        super().__init__()
+        self.heads = heads
+        self.scale = (dim // heads) ** -0.5
+        self.to_q = nn.Linear(dim, dim, bias=False)
+        self.to_k = nn.Linear(dim, dim, bias=False)
+        self.to_v = nn.Linear(dim, dim, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(dim, dim), nn.Dropout(0.0)])
+        self.pos_encoder = _PositionalEncoding(dim, max_len) if max_len else None
+        self.attention_mode = "Temporal"
+        self.is_cross_attention = False
+        self.group_norm = self.spatial_norm = self.norm_cross = None
+        self.residual_connection, self.rescale_output_factor = False, 1.0
+        self.processor = B200TemporalAttnProcessor()
+        self._qkv = _FusedWeights()
+
+    def set_processor(self, processor, _remove_lora=False):
+        if isinstance(getattr(self, "processor", None), nn.Module) and not isinstance(processor, nn.Module):
+            self._modules.pop("processor", None)
+        self.processor = processor
+
+    def get_processor(self, return_deprecated_lora: bool = False):
+        return self.processor
+
+    def native(self, n_tok: torch.Tensor, residual: torch.Tensor, b: int, f: int, d: int) -> torch.Tensor:
+        """to_out(attn(qkv(n_tok))) + residual on token-major rows (n_tok already LayerNorm'd + PE-added)."""
+        c = n_tok.shape[-1]
+        if not isinstance(self.processor, B200TemporalAttnProcessor):
+            # a foreign processor was installed (e.g. ip_adapter.py:95-126 overwrites every processor):
+            # honour the AttentionProcessor protocol in the reference's "(b d) f c" order.
+            x = n_tok.reshape(b, f, d, c).permute(0, 2, 1, 3).reshape(b * d, f, c)
+            o = self.processor(self, x, encoder_hidden_states=None, attention_mask=None)
+            return o.reshape(b, d, f, c).permute(0, 2, 1, 3).reshape(b * f * d, c) + residual
+        wqkv = self._qkv.get(self.to_q.weight, self.to_k.weight, self.to_v.weight)
+        qkv = ops.linear(n_tok, wqkv)
+        o = ops.temporal_attention_core(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], batch=b, frames=f, sites=d,
+                                        heads=self.heads, scale=self.scale)
+        return ops.linear(o, self.to_out[0].weight, f32(self.to_out[0].bias), residual=residual)
+
+
+class _GEGLU(nn.Module):
+    def __init__(self, dim, inner):
+        super().__init__()
+        self.proj = nn.Linear(dim, inner * 2)
+
+
+class FeedForward(nn.Module):
+    """diffusers FeedForward(geglu) container: net.0.proj [8C, C], net.2 [C, 4C]."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.net = nn.ModuleList([_GEGLU(dim, 4 * dim), nn.Dropout(0.0), nn.Linear(4 * dim, dim)])
+
+    def native(self, n_tok: torch.Tensor, residual: torch.Tensor) -> torch.Tensor:
+        u = ops.linear(n_tok, self.net[0].proj.weight, f32(self.net[0].proj.bias), geglu=True)
+        return ops.linear(u, self.net[2].weight, f32(self.net[2].bias), residual=residual)
+
+
+class _TemporalTransformerBlock(nn.Module):
+    def __init__(self, dim, heads, n_attn, max_len):
+        super().__init__()
+        self.attention_blocks = nn.ModuleList([TemporalAttention(dim, heads, max_len) for _ in range(n_attn)])
+        self.norms = nn.ModuleList([nn.LayerNorm(dim) for _ in range(n_attn)])
+        self.ff = FeedForward(dim)
+        self.ff_norm = nn.LayerNorm(dim)
+
+    def native(self, h: torch.Tensor, b: int, f: int, d: int) -> torch.Tensor:
+        for attn, norm in zip(self.attention_blocks, self.norms):            # motion_module.py:213-219
+            pe = attn.pos_encoder.pe if attn.pos_encoder is not None else None
+            n = ops.layernorm_pe(h, f32(norm.weight), f32(norm.bias), norm.eps, pe=f32(pe), frames=f, sites=d)
+            h = attn.native(n, h, b, f, d)
+        n = ops.layernorm_pe(h, f32(self.ff_norm.weight), f32(self.ff_norm.bias), self.ff_norm.eps)
+        return self.ff.native(n, h)                                          # :221
+
+
+class _TemporalTransformer3D(nn.Module):
+    def __init__(self, channels, heads, num_layers, n_attn, max_len, norm_num_groups=32):
+        super().__init__()
+        self.norm = nn.GroupNorm(norm_num_groups, channels, eps=1e-6, affine=True)
+        self.proj_in = nn.Linear(channels, channels)
+        self.transformer_blocks = nn.ModuleList(
+            [_TemporalTransformerBlock(channels, heads, n_attn, max_len) for _ in range(num_layers)])
+        self.proj_out = nn.Linear(channels, channels)
+
+
+class B200MotionModule(nn.Module):
+    """Drop-in for VanillaTemporalModule (reference motion_module.py:50-84): same ctor kwargs, same
+    state_dict keys (so animatediff/utils/util.py:117-120 `load_weights` works), same forward signature.
+
+    forward(input_tensor [b,C,f,h,w], temb, encoder_hidden_states, attention_mask=None, anchor_frame_idx=None)
+    """
+
+    def __init__(self, in_channels, num_attention_heads=8, num_transformer_block=2,
+                 attention_block_types=("Temporal_Self", "Temporal_Self"), cross_frame_attention_mode=None,
+                 temporal_position_encoding=False, temporal_position_encoding_max_len=24,
+                 temporal_attention_dim_div=1, zero_initialize=True):
+        super().__init__()
+        if any(t != "Temporal_Self" for t in attention_block_types):
+            raise ValueError("only Temporal_Self attention blocks exist in the shipped motion modules")
+        if temporal_attention_dim_div != 1:
+            raise ValueError("temporal_attention_dim_div != 1 is not supported")
+        self.temporal_transformer = _TemporalTransformer3D(
+            in_channels, num_attention_heads, num_transformer_block, len(attention_block_types),
+            temporal_position_encoding_max_len if temporal_position_encoding else None)
+        if zero_initialize:
+            nn.init.zeros_(self.temporal_transformer.proj_out.weight)
+            nn.init.zeros_(self.temporal_transformer.proj_out.bias)
+
+    def native(self, x4: torch.Tensor, frames: int) -> torch.Tensor:
+        """x4: channels_last [(b f), C, h, w] -> same."""
+        tt = self.temporal_transformer
+        n, c, h, w = x4.shape
+        b, d = n // frames, h * w
+        x4 = _cl(x4)
+        x_tok = tokens(x4)
+        g = tokens(group_norm(x4, tt.norm, frames, per_frame=True, silu=False))           # motion_module.py:144
+        hdn = ops.linear(g, tt.proj_in.weight, f32(tt.proj_in.bias))                       # :147
+        for blk in tt.transformer_blocks:
+            hdn = blk.native(hdn, b, frames, d)
+        y = ops.linear(hdn, tt.proj_out.weight, f32(tt.proj_out.bias), residual=x_tok)     # :155-158
+        return from_tokens(y, n, h, w)
+
+    def forward(self, input_tensor, temb=None, encoder_hidden_states=None, attention_mask=None, anchor_frame_idx=None):
+        if input_tensor.dim() != 5:
+            raise ValueError(f"Expected hidden_states to have ndim=5, but got ndim={input_tensor.dim()}.")
+        native_in = ops.video_layout(input_tensor) == L.CA_LAYOUT_BFHWC
+        x5 = to_native(input_tensor)
+        y5 = video5(self.native(frames4(x5), x5.shape[2]), x5.shape[2])
+        return y5 if native_in else y5.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# B4: ResnetBlock3D
+# --------------------------------------------------------------------------------------------------
+class InflatedGroupNormParams(nn.GroupNorm):
+    """Parameter holder (keys weight/bias) for InflatedGroupNorm / nn.GroupNorm (resnet.py:23-31)."""
+
+    def forward(self, x):  # pragma: no cover - arithmetic lives in kernel (2)
+        raise RuntimeError("GroupNorm runs inside the fused ca_groupnorm_silu kernel")
+
+
+class B200ResnetBlock3D(nn.Module):
+    """Drop-in for ResnetBlock3D (reference resnet.py:111-218): norm1+SiLU and (+temb) norm2+SiLU are one
+    fused kernel each; the convolutions stay cuDNN (channels_last, no rearrange copies)."""
+
+    def __init__(self, *, in_channels, out_channels=None, temb_channels=512, groups=32, groups_out=None, eps=1e-6,
+                 output_scale_factor=1.0, use_in_shortcut=None, use_inflated_groupnorm=True, **unused):
+        super().__init__()
+        out_channels = in_channels if out_channels is None else out_channels
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.output_scale_factor = output_scale_factor
+        self.per_frame = bool(use_inflated_groupnorm)
+        self.norm1 = InflatedGroupNormParams(groups, in_channels, eps=eps, affine=True)
+        self.conv1 = nn.Conv2d(in_channels, out_channels, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb_channels, out_channels) if temb_channels is not None else None
+        self.norm2 = InflatedGroupNormParams(groups_out or groups, out_channels, eps=eps, affine=True)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, 3, padding=1)
+        use_in_shortcut = in_channels != out_channels if use_in_shortcut is None else use_in_shortcut
+        self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1) if use_in_shortcut else None
+
+    def native(self, x4: torch.Tensor, temb: Optional[torch.Tensor], frames: int) -> torch.Tensor:
+        h = group_norm(x4, self.norm1, frames, per_frame=self.per_frame, silu=True)        # resnet.py:191-192
+        h = self.conv1(h)                                                                  # :194
+        t = None
+        if temb is not None and self.time_emb_proj is not None:
+            t = self.time_emb_proj(F.silu(temb)).float()                                   # :196-197 ([b, C], tiny)
+        h = group_norm(h, self.norm2, frames, per_frame=self.per_frame, silu=True, temb=t)  # :199-208 fused
+        h = self.conv2(h)                                                                  # :211
+        if self.conv_shortcut is not None:
+            x4 = self.conv_shortcut(x4)                                                    # :213-214
+        out = x4 + h
+        return out if self.output_scale_factor == 1.0 else out / self.output_scale_factor
+
+    def forward(self, input_tensor, temb):
+        native_in = ops.video_layout(input_tensor) == L.CA_LAYOUT_BFHWC
+        x5 = to_native(input_tensor)
+        y5 = video5(self.native(frames4(x5), temb, x5.shape[2]), x5.shape[2])
+        return y5 if native_in else y5.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# Spatial transformer (reference attention.py:52-167, 170-300).  Row N2 of SURVEY §8f: the h*w-token
+# attention core is still a library call (torch SDPA); norms and every projection run on our kernels.
+# --------------------------------------------------------------------------------------------------
+class _SpatialAttention(nn.Module):
+    def __init__(self, dim, heads, cross_dim=None):
+        super().__init__()
+        self.heads = heads
+        self.scale = (dim // heads) ** -0.5
+        cd = dim if cross_dim is None else cross_dim
+        self.is_cross = cross_dim is not None
+        self.to_q = nn.Linear(dim, dim, bias=False)
+        self.to_k = nn.Linear(cd, dim, bias=False)
+        self.to_v = nn.Linear(cd, dim, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(dim, dim), nn.Dropout(0.0)])
+        self.processor = None
+        self._fused = _FusedWeights()
+
+    def set_processor(self, processor, _remove_lora=False):
+        self.processor = processor
+
+    def get_processor(self, return_deprecated_lora: bool = False):
+        return self.processor
+
+    def native(self, n_tok, residual, n_frames, d, ctx=None, ctx_map=None):
+        c = n_tok.shape[-1]
+        hd = c // self.heads
+        if not self.is_cross:
+            qkv = ops.linear(n_tok, self._fused.get(self.to_q.weight, self.to_k.weight, self.to_v.weight))
+            qkv = qkv.reshape(n_frames, d, 3, self.heads, hd)
+            q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))
+        else:
+            q = ops.linear(n_tok, self.to_q.weight).reshape(n_frames, d, self.heads, hd).transpose(1, 2)
+            kv = ops.linear(ctx, self._fused.get(self.to_k.weight, self.to_v.weight))     # [B_ctx, L, 2C], once per prompt
+            kv = kv.reshape(ctx.shape[0], ctx.shape[1], 2, self.heads, hd)
+            kv = kv[ctx_map] if ctx_map is not None else kv
+            k, v = kv[:, :, 0].transpose(1, 2), kv[:, :, 1].transpose(1, 2)
+            if k.shape[0] != n_frames:
+                k = k.repeat_interleave(n_frames // k.shape[0], dim=0)
+                v = v.repeat_interleave(n_frames // v.shape[0], dim=0)
+        o = F.scaled_dot_product_attention(q, k, v, scale=self.scale)                       # library (N2)
+        o = o.transpose(1, 2).reshape(n_frames * d, c)
+        return ops.linear(o, self.to_out[0].weight, f32(self.to_out[0].bias), residual=residual)
+
+
+class _BasicTransformerBlock(nn.Module):
+    def __init__(self, dim, heads, cross_dim):
+        super().__init__()
+        self.attn1 = _SpatialAttention(dim, heads)
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn2 = _SpatialAttention(dim, heads, cross_dim)
+        self.norm2 = nn.LayerNorm(dim)
+        self.ff = FeedForward(dim)
+        self.norm3 = nn.LayerNorm(dim)
+        self.processor = None  # the reference block subclasses Attention (attention.py:170) and so is enumerated too
+
+    def set_processor(self, processor, _remove_lora=False):
+        self.processor = processor
+
+    def get_processor(self, return_deprecated_lora: bool = False):
+        return self.processor
+
+    def native(self, h, n_frames, d, ctx, ctx_map):
+        ln = lambda x, m: ops.layernorm_pe(x, f32(m.weight), f32(m.bias), m.eps)  # noqa: E731
+        h = self.attn1.native(ln(h, self.norm1), h, n_frames, d)                            # attention.py:268-271
+        h = self.attn2.native(ln(h, self.norm2), h, n_frames, d, ctx, ctx_map)              # :273-286
+        return self.ff.native(ln(h, self.norm3), h)                                         # :289
+
+
+class SpatialTransformer3D(nn.Module):
+    """Transformer3DModel mirror (use_linear_projection False: proj_in/out are 1x1 convs == token GEMMs)."""
+
+    def __init__(self, heads, in_channels, cross_attention_dim, norm_num_groups=32):
+        super().__init__()
+        self.norm = nn.GroupNorm(norm_num_groups, in_channels, eps=1e-6, affine=True)
+        self.proj_in = nn.Conv2d(in_channels, in_channels, 1)
+        self.transformer_blocks = nn.ModuleList([_BasicTransformerBlock(in_channels, heads, cross_attention_dim)])
+        self.proj_out = nn.Conv2d(in_channels, in_channels, 1)
+
+    def native(self, x4, frames, ctx, ctx_map=None):
+        n, c, h, w = x4.shape
+        x4 = _cl(x4)
+        x_tok = tokens(x4)
+        g = tokens(group_norm(x4, self.norm, frames, per_frame=True, silu=False))           # attention.py:131
+        hdn = ops.linear(g, self.proj_in.weight.reshape(c, c), f32(self.proj_in.bias))       # :133
+        for blk in self.transformer_blocks:
+            hdn = blk.native(hdn, n, h * w, ctx, ctx_map)
+        y = ops.linear(hdn, self.proj_out.weight.reshape(c, c), f32(self.proj_out.bias), residual=x_tok)  # :157-162
+        return from_tokens(y, n, h, w)

@@ -12,6 +12,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib as L
+from . import profiler as P
 
 _DTYPES = {torch.bfloat16: L.CA_BF16, torch.float16: L.CA_F16, torch.float32: L.CA_F32}
 
@@ -87,9 +88,10 @@ def groupnorm_silu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, gro
     lib = L.load()
     nws = lib.ca_groupnorm_workspace_bytes(b, c, f, h, w, groups, int(per_frame), layout, _dt(x))
     ws = _workspace(nws, x.device)
-    L.check(lib.ca_groupnorm_silu(x.data_ptr(), y.data_ptr(), g32.data_ptr(), b32.data_ptr(), _ptr(t32), b, c, f, h, w,
-                                  groups, float(eps), int(per_frame), int(silu), layout, _dt(x), _ptr(ws),
-                                  0 if ws is None else ws.numel(), _stream()), "ca_groupnorm_silu")
+    with P.span("groupnorm_silu", 1, 2.0 * x.numel() * x.element_size()):
+        L.check(lib.ca_groupnorm_silu(x.data_ptr(), y.data_ptr(), g32.data_ptr(), b32.data_ptr(), _ptr(t32), b, c, f, h, w,
+                                      groups, float(eps), int(per_frame), int(silu), layout, _dt(x), _ptr(ws),
+                                      0 if ws is None else ws.numel(), _stream()), "ca_groupnorm_silu")
     return y
 
 
@@ -110,8 +112,9 @@ def layernorm_pe(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: 
             raise ValueError(f"video has {frames} frames but the positional encoding only {pe32.shape[0]} (motion_module.py:236)")
         if rows % (frames * sites) != 0:
             raise ValueError("rows must be b*frames*sites")
-    L.check(L.load().ca_layernorm_pe(x.data_ptr(), y.data_ptr(), g32.data_ptr(), b32.data_ptr(), _ptr(pe32), rows, c,
-                                     frames, sites, float(eps), _dt(x), _stream()), "ca_layernorm_pe")
+    with P.span("layernorm_pe", 1, 2.0 * x.numel() * x.element_size()):
+        L.check(L.load().ca_layernorm_pe(x.data_ptr(), y.data_ptr(), g32.data_ptr(), b32.data_ptr(), _ptr(pe32), rows, c,
+                                         frames, sites, float(eps), _dt(x), _stream()), "ca_layernorm_pe")
     return y
 
 
@@ -137,9 +140,10 @@ def temporal_attention_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *
     if o.stride(1) != 1 or o.shape != q.shape:
         raise ValueError("bad out tensor")
     scale = hd ** -0.5 if scale is None else scale
-    L.check(L.load().ca_temporal_attn_core(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), batch, frames, sites,
-                                           heads, hd, q.stride(0), k.stride(0), v.stride(0), o.stride(0), int(seq_major),
-                                           float(scale), _dt(q), _stream()), "ca_temporal_attn_core")
+    with P.span("temporal_attn_core", 1, 4.0 * T * Cq * q.element_size(), 4.0 * frames * Cq * T):
+        L.check(L.load().ca_temporal_attn_core(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), batch, frames, sites,
+                                               heads, hd, q.stride(0), k.stride(0), v.stride(0), o.stride(0), int(seq_major),
+                                               float(scale), _dt(q), _stream()), "ca_temporal_attn_core")
     return o
 
 
@@ -193,8 +197,10 @@ def residual_merge(per_net: Sequence[Sequence[torch.Tensor]], scales: Sequence[S
                 raise ValueError("residual batch sizes differ")
             res_ptrs[k * n_res + i] = r.data_ptr()
             sc[k * n_res + i] = float(scales[k][i])
-    L.check(L.load().ca_residual_merge(res_ptrs, sc, dst_ptrs, chw, n_nets, n_res, b_res, b_dst, frames, int(add_into_dst),
-                                       layout, _DTYPES[dtype], _stream()), "ca_residual_merge")
+    nbytes = sum((n_nets * (d.numel() // b_dst) * b_res + (2 if add_into_dst else 1) * d.numel()) * d.element_size() for d in dst)
+    with P.span("residual_merge", 1, float(nbytes)):
+        L.check(L.load().ca_residual_merge(res_ptrs, sc, dst_ptrs, chw, n_nets, n_res, b_res, b_dst, frames, int(add_into_dst),
+                                           layout, _DTYPES[dtype], _stream()), "ca_residual_merge")
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, residual: Optional[torch.Tensor] = None,
@@ -225,7 +231,10 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     b32 = _f32(bias)
     if b32 is not None and b32.numel() != n:
         raise ValueError("linear: bias must be [n]")
-    L.check(L.load().ca_linear(x2.data_ptr(), w.data_ptr(), _ptr(b32), _ptr(r2), y.data_ptr(), m, n, k, x2.stride(0),
-                               0 if r2 is None else r2.stride(0), y.stride(0), L.CA_EPI_GEGLU if geglu else L.CA_EPI_NONE,
-                               _dt(x), _stream()), "ca_linear")
+    es = x.element_size()
+    nbytes = (m * k + n * k + m * n_out * (2 if r2 is not None else 1)) * es
+    with P.span("linear_tcgen05", 1, float(nbytes), 2.0 * m * n * k):
+        L.check(L.load().ca_linear(x2.data_ptr(), w.data_ptr(), _ptr(b32), _ptr(r2), y.data_ptr(), m, n, k, x2.stride(0),
+                                   0 if r2 is None else r2.stride(0), y.stride(0), L.CA_EPI_GEGLU if geglu else L.CA_EPI_NONE,
+                                   _dt(x), _stream()), "ca_linear")
     return y.reshape(*lead, n_out)

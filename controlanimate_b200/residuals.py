@@ -1,0 +1,117 @@
+"""Boundary B3: the ControlNet residual contract.
+
+Two ways to honour `down_block_additional_residuals` (12) / `mid_block_additional_residual`:
+
+* `merge_controlnet_residuals(...)` — contract-preserving producer: reads the N per-net RAW residual lists and
+  writes ONE merged set directly in the reference's [b, c, f, h, w] layout (absorbs the per-net conditioning
+  scale, the guess-mode log-spaced factors, the sum over nets and the 13 '(b f) c h w -> b c f h w' rearranges of
+  modules/controlresiduals_pipeline.py:294-312): (N+1)·E·s bytes of HBM traffic.
+* `ResidualSet` — lazy set (per-net raw tensors + scales) that `UNet3DConditionModel.forward` folds straight into
+  its skip tensors in place, `skip_i += Σ_k s_k r_{k,i}` (also replaces unet.py:567-576, 584-585): (N+2)·E·s bytes,
+  nothing materialised.  Plain tuples of merged tensors are still accepted by the UNet.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+N_RESIDUALS = 13
+
+
+def guess_mode_factors(n: int = N_RESIDUALS) -> List[float]:
+    """diffusers ControlNetModel guess-mode scaling: logspace(-1, 0, n), mid residual takes the last factor."""
+    return [float(v) for v in torch.logspace(-1, 0, n)]
+
+
+def _scales(cond_scale: Sequence[float], n_res: int, guess_mode: bool) -> List[List[float]]:
+    level = guess_mode_factors(n_res) if guess_mode else [1.0] * n_res
+    return [[level[i] * float(s) for i in range(n_res)] for s in cond_scale]
+
+
+class ResidualSet:
+    """Per-net raw residuals [(b f), c_i, h_i, w_i] (12 down + mid, in UNet skip order) + per-net scales."""
+
+    def __init__(self, per_net: Sequence[Sequence[torch.Tensor]], cond_scale: Sequence[float], frames: int,
+                 guess_mode: bool = False):
+        if len(per_net) != len(cond_scale) or len(per_net) == 0:
+            raise ValueError("one conditioning scale per ControlNet is required")
+        self.per_net = [list(r) for r in per_net]
+        self.n_res = len(self.per_net[0])
+        self.frames = frames
+        self.scales = _scales(cond_scale, self.n_res, guess_mode)
+        # native nets emit channels_last tensors; diffusers-style nets emit NCHW-contiguous ones
+        t = self.per_net[0][1] if self.n_res > 1 else self.per_net[0][0]
+        self.layout = L.CA_LAYOUT_BFHWC if t.is_contiguous(memory_format=torch.channels_last) else L.CA_LAYOUT_NCFHW
+
+    @staticmethod
+    def coerce(down, mid, frames) -> Optional["ResidualSet"]:
+        """Accept what the reference loop passes (controlanimation_pipeline.py:836-841): None, a ResidualSet in the
+        `down` slot, or plain merged [b,c,f,h,w] tuples."""
+        if down is None and mid is None:
+            return None
+        if isinstance(down, ResidualSet):
+            return down
+        return _MergedResiduals(list(down), mid, frames)
+
+    def add_into(self, skips: Optional[Sequence[torch.Tensor]], mid: Optional[torch.Tensor]) -> None:
+        """skips: 12 channels_last [(b f), c, h, w] tensors (in place); mid: the mid-block output (in place)."""
+        if self.layout == L.CA_LAYOUT_NCFHW:
+            # diffusers-style NCHW residuals against native (BFHWC) skips: merge once into the reference layout
+            # (one kernel, contract-preserving) and add that; the single-pass path needs native residuals.
+            if getattr(self, "_merged", None) is None:
+                self._merged = _MergedResiduals(*self._materialize_lists(), self.frames)
+            return self._merged.add_into(skips, mid)
+        if skips is not None:
+            k = len(skips)
+            ops.residual_merge([r[:k] for r in self.per_net], [s[:k] for s in self.scales], list(skips),
+                               frames=self.frames, add_into_dst=True, layout=self.layout)
+        if mid is not None:
+            ops.residual_merge([r[-1:] for r in self.per_net], [s[-1:] for s in self.scales], [mid],
+                               frames=self.frames, add_into_dst=True, layout=self.layout)
+
+    def materialize(self) -> Tuple[Tuple[torch.Tensor, ...], torch.Tensor]:
+        return merge_controlnet_residuals(self.per_net, None, self.frames, scales=self.scales)
+
+    def _materialize_lists(self):
+        down, mid = self.materialize()
+        return list(down), mid
+
+
+class _MergedResiduals(ResidualSet):
+    """Already-merged tensors in the reference layout [b, c, f, h, w] (the plain B3 contract)."""
+
+    def __init__(self, down, mid, frames):
+        self.down, self.mid, self.frames = down, mid, frames
+
+    def add_into(self, skips, mid):
+        from .layers import video5
+        if skips is not None:
+            for s, r in zip(skips, self.down):
+                video5(s, self.frames).add_(r.to(s.dtype))     # strided elementwise add, batch broadcast as unet.py:572
+        if mid is not None and self.mid is not None:
+            video5(mid, self.frames).add_(self.mid.to(mid.dtype))
+
+
+def merge_controlnet_residuals(per_net: Sequence[Sequence[torch.Tensor]], cond_scale: Optional[Sequence[float]], frames: int,
+                               guess_mode: bool = False, scales=None) -> Tuple[Tuple[torch.Tensor, ...], torch.Tensor]:
+    """Per-net raw residual lists ([(b f), c, h, w], NCHW-contiguous as diffusers ControlNets emit them) ->
+    (down_block_additional_residuals[12], mid_block_additional_residual) in [b, c, f, h, w] (one kernel launch)."""
+    n_res = len(per_net[0])
+    scales = _scales(cond_scale, n_res, guess_mode) if scales is None else scales
+    first = per_net[0]
+    nchw = first[0].is_contiguous()
+    layout = L.CA_LAYOUT_NCFHW if nchw else L.CA_LAYOUT_BFHWC
+    dst = []
+    for r in first:
+        n, c, h, w = r.shape
+        b = n // frames
+        if nchw:
+            dst.append(torch.empty((b, c, frames, h, w), dtype=r.dtype, device=r.device))
+        else:
+            dst.append(torch.empty((b, frames, h, w, c), dtype=r.dtype, device=r.device).permute(0, 4, 1, 2, 3))
+    ops.residual_merge(per_net, scales, dst, frames=frames, add_into_dst=False, layout=layout)
+    return tuple(dst[:-1]), dst[-1]

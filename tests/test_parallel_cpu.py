@@ -1,0 +1,86 @@
+"""world_size-2/3 gloo tests (CPU) of the multi-GPU host logic in controlanimate_b200/parallel.py."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from controlanimate_b200 import parallel as P
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _run(fn, world):
+    port = _free_port()
+    mp.spawn(_entry, args=(fn, world, port), nprocs=world, join=True)
+
+
+def _entry(rank, fn, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        fn(rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+def _full_clip(n_frames):
+    g = torch.Generator().manual_seed(5)
+    return torch.randn(1, 4, n_frames, 6, 5, generator=g)
+
+
+def _window_worker(rank, world):
+    frames, ov = 8, 2
+    starts = P.window_starts(world, frames, ov)
+    wins = []
+    for w, s in enumerate(starts):       # every window perturbs its copy so the overlap frames really differ
+        wins.append(_full_clip(starts[-1] + frames)[:, :, s:s + frames] + 0.1 * w)
+    want = P.blend_windows_reference(wins, ov)
+    got = P.WindowParallel(rank, world, frames, ov).exchange(wins[rank])
+    assert torch.allclose(got, want[rank], atol=1e-6)
+    # interior frames are untouched
+    assert torch.equal(got[:, :, ov:frames - ov], wins[rank][:, :, ov:frames - ov])
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_window_parallel_exchange(world):
+    _run(_window_worker, world)
+
+
+def _cfg_worker(rank, world):
+    g = torch.Generator().manual_seed(9)
+    noise = torch.randn(2, 4, 3, 4, 4, generator=g)
+    cfg = P.CFGParallel(rank, world)
+    out = cfg.combine(cfg.my_rows(noise), 7.5)
+    u, c = noise.chunk(2)
+    assert torch.allclose(out, u + 7.5 * (c - u), atol=1e-6)
+
+
+def test_cfg_parallel():
+    _run(_cfg_worker, 2)
+
+
+def _cn_worker(rank, world):
+    n_nets = 3
+    g = torch.Generator().manual_seed(11)
+    sets = [[torch.randn(4, 8, 3, 3, generator=g), torch.randn(4, 16, 2, 2, generator=g)] for _ in range(n_nets)]
+    cp = P.ControlNetParallel(rank, world, n_nets)
+    assert sorted(sum(([k for k in range(n_nets) if k % world == r] for r in range(world)), [])) == [0, 1, 2]
+    got = cp.gather([sets[k] for k in cp.my_nets()])
+    for k in range(n_nets):
+        for a, b in zip(got[k], sets[k]):
+            assert torch.equal(a, b)
+
+
+def test_controlnet_parallel_gather():
+    _run(_cn_worker, 2)
+
+
+def test_window_starts_match_config3():
+    assert P.window_starts(5, 16, 4) == [0, 12, 24, 36, 48]
