@@ -195,7 +195,7 @@ def run_b200(args):
     mc = pipeline.MultiControlNetResiduals(nets, COND_SCALE)
     sched = pipeline.DDIMScheduler()
     timesteps = sched.set_timesteps(DDIM_STEPS)
-    loop = pipeline.DenoisingLoop(unet, mc, sched, guidance_scale=GUIDANCE)
+    loop = pipeline.DenoisingLoop(unet, mc, sched, guidance_scale=GUIDANCE, use_cuda_graph=not args.no_graph)
     windows = parallel.WindowParallel(rank, world, FRAMES, OVERLAP) if world > 1 else None
 
     f, lat = FRAMES, args.latent
@@ -266,10 +266,11 @@ def run_b200(args):
     # ---- per-kernel timing pass (CUDA events around every C-ABI launch, on the launching stream) ---------------
     kern = None
     if rank == 0:
-        profiler.enable(True)
-        lat2 = latents
-        for i in range(2):
-            lat2 = loop.step(lat2, timesteps[i], d_prompt)
+        loop.use_cuda_graph = False                # eager: every launch bracketed by events, GPU kept backlogged
+        lat2 = loop.step(latents, timesteps[0], d_prompt)
+        torch.cuda.synchronize()
+        profiler.enable(True, backlog_ms=400.0)
+        lat2 = loop.step(lat2, timesteps[1], d_prompt)
         torch.cuda.synchronize()
         kern = profiler.summary(measured_peaks())
         profiler.enable(False)
@@ -287,7 +288,10 @@ def run_b200(args):
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h_latents.numel() * 4 + h_prompt.numel() * 2, "d2h_bytes_per_step": h_out.numel() * 4},
-            "gpu_launches": launches,
+            # kernels of libca_b200.so executed inside the timed region (counted per launch in eager mode; with CUDA-graph
+            # replay = launches recorded in one captured step x timed steps)
+            "gpu_launches": launches if launches else kern["launches_per_step"] * args.steps,
+            "cuda_graph": not args.no_graph,
             "roofline": top,
             "kernels": kern["families"],
             "own_kernel_share_of_step": kern["own_share"],
@@ -315,6 +319,7 @@ def main():
     ap.add_argument("--latent", type=int, default=LATENT)
     ap.add_argument("--cpu-frames", type=int, default=1, help="frames of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

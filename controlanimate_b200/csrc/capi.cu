@@ -1,7 +1,9 @@
 // Library-wide pieces of the C ABI: error text, device query, tensor-map encoder.
 #include <stdarg.h>
 
+#include <map>
 #include <mutex>
+#include <tuple>
 
 #include "common.cuh"
 #include "tma.cuh"
@@ -27,6 +29,36 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+static std::mutex g_cache_mu;
+
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes) {
+  static std::map<std::pair<int, const void*>, size_t> limit;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  size_t& cur = limit[{dev, func}];
+  if (bytes <= cur) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
+
+cudaError_t cached_occupancy(int* per_sm, const void* func, int threads, size_t smem) {
+  static std::map<std::tuple<int, const void*, int, size_t>, int> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  auto key = std::make_tuple(dev, func, threads, smem);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *per_sm = it->second;
+    return cudaSuccess;
+  }
+  const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, func, threads, smem);
+  if (e == cudaSuccess) cache[key] = *per_sm;
+  return e;
 }
 
 EncodeTiledFn get_encode_tiled() {

@@ -13,6 +13,9 @@ namespace ca {
 // ---- error plumbing (host) ----------------------------------------------------------------
 void set_error(const char* fmt, ...);
 int sm_count();
+// Raise a kernel's dynamic shared-memory limit once per (device, function); cached occupancy query.
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes);
+cudaError_t cached_occupancy(int* per_sm, const void* func, int threads, size_t smem);
 
 #define CA_CHECK_ARG(cond, ...)           \
   do {                                    \
@@ -53,20 +56,52 @@ struct Traits<float> {
   __device__ static float from_f(float v) { return v; }
 };
 
-// 16-byte vector of T, unpacked to / packed from fp32.
+// 16-byte vector of T, unpacked to / packed from fp32 with register-only bit manipulation (no address of the
+// vector is ever taken, so arrays of Vec16 stay in registers).
+__device__ __forceinline__ void unpack2(uint32_t w, float& lo, float& hi, __nv_bfloat16) {
+  lo = __uint_as_float(w << 16);
+  hi = __uint_as_float(w & 0xffff0000u);
+}
+__device__ __forceinline__ void unpack2(uint32_t w, float& lo, float& hi, __half) {
+  const __half2 h = *reinterpret_cast<const __half2*>(&w);
+  const float2 f = __half22float2(h);
+  lo = f.x;
+  hi = f.y;
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi, __nv_bfloat16) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi, __half) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 template <typename T>
 struct Vec16 {
   static constexpr int N = Traits<T>::kVec;
   uint4 raw;
-  __device__ void unpack(float (&f)[N]) const {
-    const T* p = reinterpret_cast<const T*>(&raw);
-#pragma unroll
-    for (int i = 0; i < N; ++i) f[i] = Traits<T>::to_f(p[i]);
+  __device__ __forceinline__ void unpack(float (&f)[N]) const {
+    if constexpr (N == 4) {
+      f[0] = __uint_as_float(raw.x);
+      f[1] = __uint_as_float(raw.y);
+      f[2] = __uint_as_float(raw.z);
+      f[3] = __uint_as_float(raw.w);
+    } else {
+      unpack2(raw.x, f[0], f[1], T());
+      unpack2(raw.y, f[2], f[3], T());
+      unpack2(raw.z, f[4], f[5], T());
+      unpack2(raw.w, f[6], f[7], T());
+    }
   }
-  __device__ void pack(const float (&f)[N]) {
-    T* p = reinterpret_cast<T*>(&raw);
-#pragma unroll
-    for (int i = 0; i < N; ++i) p[i] = Traits<T>::from_f(f[i]);
+  __device__ __forceinline__ void pack(const float (&f)[N]) {
+    if constexpr (N == 4) {
+      raw = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+    } else {
+      raw = make_uint4(pack2(f[0], f[1], T()), pack2(f[2], f[3], T()), pack2(f[4], f[5], T()), pack2(f[6], f[7], T()));
+    }
   }
 };
 

@@ -13,7 +13,8 @@
 //   warp 1   MMA issuer   : one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN<=256,
 //                           K=16) x4 per stage; tcgen05.commit releases the smem stage / publishes the accumulator
 //   warp 2   TMEM allocator (512 columns = two accumulator stages of up to 256 fp32 columns)
-//   warps 4-7 epilogue    : tcgen05.ld (32 lanes x 16 columns) -> +bias -> [GEGLU] -> +residual -> bf16 -> global;
+//   warps 4-19 epilogue   : tcgen05.ld -> +bias -> [GEGLU] -> +residual (register-prefetched) -> bf16 ->
+//                           SWIZZLE_64B smem staging box -> TMA tensor store;
 //                           overlaps the MMA of the next tile through the second TMEM stage.
 // Both operands are K-major ("TN"): x rows and nn.Linear weight rows are contiguous along k, so the TMA
 // box lands directly in the canonical UMMA SWIZZLE_128B layout (8-row x 128-byte atoms, SBO = 1024 B).
@@ -29,7 +30,10 @@ constexpr int BM = 128;       // UMMA_M
 constexpr int BK = 64;        // one 128-byte swizzle atom of 16-bit elements
 constexpr int UMMA_K = 16;
 constexpr int kAccCols = 256; // TMEM columns per accumulator stage
-constexpr int kThreads = 256;
+constexpr int kEpiParts = 4;            // epilogue warps per TMEM lane quarter
+constexpr int kEpiWarps = 4 * kEpiParts;
+constexpr int kEpiBytesPerWarp = 4096;  // 2 x 2 KB output staging boxes
+constexpr int kThreads = 128 + 32 * kEpiWarps;  // 4 control warps (TMA, MMA, TMEM alloc, spare) + 16 epilogue warps
 
 struct GemmParams {
   long long m;
@@ -90,7 +94,19 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
+// GELU with the exact-erf definition (diffusers GEGLU uses F.gelu default); erf by Abramowitz-Stegun 7.1.26
+// (|abs err| <= 1.5e-7, far below bf16 resolution): one MUFU.RCP + one MUFU.EX2 + 8 FMA instead of libdevice erff.
+__device__ __forceinline__ float gelu_erf(float v) {
+  const float x = fabsf(v) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, x, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erfc_x = poly * t * __expf(-x * x);          // 1 - erf(|v|/sqrt2)
+  const float erf_v = copysignf(1.0f - erfc_x, v);
+  return 0.5f * v * (1.0f + erf_v);
+}
 
 template <typename T>
 __device__ __forceinline__ void store16(T* dst, const float (&v)[16]) {
@@ -124,7 +140,7 @@ __device__ __forceinline__ void load16_add(const T* src, float (&v)[16]) {
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                        const GemmParams p) {
+                        const __grid_constant__ CUtensorMap map_y, const GemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   __shared__ uint64_t full_bar[8], empty_bar[8], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_slot;
@@ -145,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -217,55 +233,122 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (TMEM -> registers -> global) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const T* __restrict__ res = reinterpret_cast<const T*>(p.residual);
-    T* __restrict__ y = reinterpret_cast<T*>(p.y);
+    // ===================== epilogue (TMEM -> registers -> swizzled smem -> TMA store), 16 warps =====================
+    // warp w: TMEM lane quarter q = w % 4 (hardware restriction), column part (w - 4) / 4 of the tile.  Work unit: a
+    // box of 32 rows x 32 output columns.  The residual row segment (64 B = two full sectors per thread) is prefetched
+    // into registers one box ahead (the first one before the accumulator is even ready); results are written as bf16
+    // into a SWIZZLE_64B staging box (conflict-free 16-byte stores: chunk ^= (row / 2) & 3) and leave through a TMA
+    // tensor store, so every global write of the epilogue is a coalesced bulk transfer clipped at the tensor edge.
+    const int q = warp & 3, part = (warp - 4) >> 2, ew = warp - 4;
     const int out_cols = p.geglu ? p.bn / 2 : p.bn;
+    const int boxes = out_cols / 32;
+    const int b_begin = (boxes * part) / kEpiParts, b_end = (boxes * (part + 1)) / kEpiParts;
+    unsigned char* stage_base = smem + (size_t)stages * stage_bytes + (size_t)ew * kEpiBytesPerWarp;
+    unsigned char* obuf[2] = {stage_base, stage_base + 2048};
+    const T* __restrict__ res = reinterpret_cast<const T*>(p.residual);
+    const int sw = (lane >> 1) & 3;  // SWIZZLE_64B xor for this thread's row
+    int ob = 0;
+    if (lane == 0) prefetch_tensormap(&map_y);
     long long it = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int nb = (int)(tile % p.num_n_blocks);
       const int mb = (int)(tile / p.num_n_blocks);
       const int acc = (int)(it & 1);
+      const int row0 = mb * BM + q * 32;   // first row of this warp's boxes
+      const int n0 = nb * out_cols;        // first output column of this tile
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kAccCols;
+      const bool live = res && (row0 + lane) < p.m;
+      const T* res_row = live ? res + (long long)(row0 + lane) * p.ldr + n0 : nullptr;
+      uint4 rres[4];
+      if (live && b_begin < b_end) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rres[j] = ldg_stream(res_row + b_begin * 32 + j * 8);
+      }
       mbar_wait(&tmem_full[acc], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      const long long row = (long long)mb * BM + q * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kAccCols;
-      const int n0 = nb * out_cols;  // first output column of this tile
-      for (int c = 0; c < out_cols; c += 16) {
-        uint32_t r[16];
-        float v[16];
-        tmem_ld16(taddr + c, r);
-        if (p.geglu) {
-          uint32_t g[16];
-          tmem_ld16(taddr + out_cols + c, g);
-          tmem_ld_wait();
+#pragma unroll 1
+      for (int bx = b_begin; bx < b_end; ++bx) {
+        const int col = bx * 32;  // column of this box inside the tile
+        // staging buffer `ob` was handed to a TMA store two boxes ago: make sure that store has read it
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float a = __uint_as_float(r[j]), gt = __uint_as_float(g[j]);
-            if (p.bias) {
-              a += __ldg(p.bias + n0 + c + j);
-              gt += __ldg(p.bias + p.n / 2 + n0 + c + j);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[16];
+          float v[16];
+          tmem_ld16(taddr + col + 16 * half, r);
+          const int gc = n0 + col + 16 * half;  // global output column
+          if (p.geglu) {
+            uint32_t g[16];
+            tmem_ld16(taddr + out_cols + col + 16 * half, g);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+              if (p.bias) {
+                ba = __ldg(reinterpret_cast<const float4*>(p.bias + gc + j));
+                bg = __ldg(reinterpret_cast<const float4*>(p.bias + p.n / 2 + gc + j));
+              }
+              v[j + 0] = (__uint_as_float(r[j + 0]) + ba.x) * gelu_erf(__uint_as_float(g[j + 0]) + bg.x);
+              v[j + 1] = (__uint_as_float(r[j + 1]) + ba.y) * gelu_erf(__uint_as_float(g[j + 1]) + bg.y);
+              v[j + 2] = (__uint_as_float(r[j + 2]) + ba.z) * gelu_erf(__uint_as_float(g[j + 2]) + bg.z);
+              v[j + 3] = (__uint_as_float(r[j + 3]) + ba.w) * gelu_erf(__uint_as_float(g[j + 3]) + bg.w);
             }
-            v[j] = a * gelu_erf(gt);
-          }
-        } else {
-          tmem_ld_wait();
+          } else {
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            v[j] = __uint_as_float(r[j]);
-            if (p.bias) v[j] += __ldg(p.bias + n0 + c + j);
+            for (int j = 0; j < 16; j += 4) {
+              float4 ba = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias) ba = __ldg(reinterpret_cast<const float4*>(p.bias + gc + j));
+              v[j + 0] = __uint_as_float(r[j + 0]) + ba.x;
+              v[j + 1] = __uint_as_float(r[j + 1]) + ba.y;
+              v[j + 2] = __uint_as_float(r[j + 2]) + ba.z;
+              v[j + 3] = __uint_as_float(r[j + 3]) + ba.w;
+            }
           }
+          if (live) {
+            Vec16<T> a, b;
+            a.raw = rres[2 * half];
+            b.raw = rres[2 * half + 1];
+            float lo[8], hi[8];
+            a.unpack(lo);
+            b.unpack(hi);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[j] += lo[j];
+              v[8 + j] += hi[j];
+            }
+          }
+          // this thread's row inside the box: 64 bytes = four 16-byte chunks, chunks 2*half and 2*half+1 here
+          Vec16<T> a, b;
+          float lo[8], hi[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            lo[j] = v[j];
+            hi[j] = v[8 + j];
+          }
+          a.pack(lo);
+          b.pack(hi);
+          *reinterpret_cast<uint4*>(obuf[ob] + lane * 64 + ((2 * half) ^ sw) * 16) = a.raw;
+          *reinterpret_cast<uint4*>(obuf[ob] + lane * 64 + ((2 * half + 1) ^ sw) * 16) = b.raw;
         }
-        if (row < p.m) {
-          if (res) load16_add(res + row * p.ldr + n0 + c, v);
-          store16(y + row * p.ldy + n0 + c, v);
+        if (live && bx + 1 < b_end) {  // residual of the next box
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rres[j] = ldg_stream(res_row + col + 32 + j * 8);
         }
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy) store
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&map_y, obuf[ob], n0 + col, row0);
+          bulk_commit();
+        }
+        ob ^= 1;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
+    if (lane == 0) bulk_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -275,8 +358,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
-int pick_bn(int n_cols, int cap) {  // largest multiple of 16 <= cap dividing n_cols
-  for (int bn = cap; bn >= 16; bn -= 16)
+int pick_bn(int n_cols, int cap) {  // largest multiple of 32 <= cap dividing n_cols (epilogue boxes are 32 columns wide)
+  for (int bn = cap; bn >= 32; bn -= 32)
     if (n_cols % bn == 0) return bn;
   return 0;
 }
@@ -295,7 +378,7 @@ extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, c
   CA_CHECK_ARG(epilogue == CA_EPI_NONE || epilogue == CA_EPI_GEGLU, "linear: unknown epilogue %d", epilogue);
   const bool geglu = epilogue == CA_EPI_GEGLU;
   CA_CHECK_ARG(k % 8 == 0 && ldx % 8 == 0 && ldx >= k, "linear: k and ldx must be multiples of 8 (16-byte TMA rows)");
-  CA_CHECK_ARG(n % (geglu ? 32 : 16) == 0, "linear: n=%d must be a multiple of %d", n, geglu ? 32 : 16);
+  CA_CHECK_ARG(n % (geglu ? 64 : 32) == 0, "linear: n=%d must be a multiple of %d", n, geglu ? 64 : 32);
   const int n_out = geglu ? n / 2 : n;
   CA_CHECK_ARG(ldy >= n_out && ldy % 8 == 0 && (!residual || (ldr >= n_out && ldr % 8 == 0)), "linear: bad ldy/ldr");
   CA_CHECK_ARG(aligned16(x) && aligned16(w) && aligned16(y) && (!residual || aligned16(residual)), "linear: pointers must be 16-byte aligned");
@@ -306,7 +389,7 @@ extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, c
   p.m = m; p.n = n; p.k = k; p.geglu = geglu ? 1 : 0; p.n_out = n_out;
   if (geglu) {
     const int half = pick_bn(n / 2, 128);
-    CA_CHECK_ARG(half >= 16, "linear: cannot tile n=%d for GEGLU", n);
+    CA_CHECK_ARG(half >= 32, "linear: cannot tile n=%d for GEGLU", n);
     p.bn = 2 * half;
     p.num_n_blocks = (n / 2) / half;
   } else {
@@ -322,11 +405,12 @@ extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, c
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
   const uint32_t stage_bytes = BM * BK * 2 + (((uint32_t)p.bn * BK * 2 + 1023) & ~1023u);
-  int stages = (int)((200 * 1024) / stage_bytes);
+  const size_t epi_bytes = (size_t)kEpiWarps * kEpiBytesPerWarp;
+  int stages = (int)((225 * 1024 - 1024 - epi_bytes) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + epi_bytes + 1024;
 
   CUtensorMap mx, mw;
   const CUtensorMapDataType dt = dtype == CA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -343,13 +427,20 @@ extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, c
     if (!encode_tensor_map(&mw, dt, 2, w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
       return CA_ERR_CUDA;
   }
+  CUtensorMap my;
+  {
+    const uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)m};
+    const uint32_t box[2] = {32, 32};
+    const uint64_t sy[1] = {(uint64_t)ldy * 2};
+    if (!encode_tensor_map(&my, dt, 2, y, dims, sy, box, CU_TENSOR_MAP_SWIZZLE_64B)) return CA_ERR_CUDA;
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long tiles = (long long)p.num_m_blocks * p.num_n_blocks;
   long long grid = sm_count();
   if (grid > tiles) grid = tiles;
   auto run = [&](auto kernel) -> int {
-    CA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<(unsigned)grid, kThreads, smem, st>>>(mx, mw, p);
+    CA_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), 226 * 1024));
+    kernel<<<(unsigned)grid, kThreads, smem, st>>>(mx, mw, my, p);
     CA_CUDA(cudaGetLastError());
     return CA_OK;
   };

@@ -389,9 +389,9 @@ extern "C" __attribute__((visibility("default"))) int ca_temporal_attn_core(cons
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int threads = (S + 1) * 32;
   auto run = [&](auto kernel) -> int {
-    CA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CA_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), 220 * 1024));
     int per_sm = 1;
-    CA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    CA_CUDA(cached_occupancy(&per_sm, reinterpret_cast<const void*>(kernel), threads, smem));
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)sm_count() * per_sm;
     if (grid > p.units) grid = p.units;

@@ -163,7 +163,14 @@ class _PositionalEncoding(nn.Module):
         # model must not quantise it)
         pe = self.pe
         super()._apply(fn, recurse)
-        self.pe = pe.to(device=self.pe.device, dtype=torch.float32)
+        dev = self.pe.device
+        if dev.type == "meta":
+            return self
+        if pe.is_meta:  # materialised from the meta device (utils.build_on_device): the table is analytic
+            from .utils import analytic_pe
+            self.pe = analytic_pe(pe.shape[1], pe.shape[2], device=dev)
+        else:
+            self.pe = pe.to(device=dev, dtype=torch.float32)
         return self
 
 

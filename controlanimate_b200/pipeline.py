@@ -84,35 +84,73 @@ class MultiControlNetResiduals:
 
 class DenoisingLoop:
     """The hot loop (controlanimation_pipeline.py:790-856) for the non-LCM path: CFG-duplicated latents, ControlNets,
-    UNet3D, `eps = eps_u + g (eps_c - eps_u)` (:845-846), scheduler step (:849).  No per-step empty_cache()."""
+    UNet3D, `eps = eps_u + g (eps_c - eps_u)` (:845-846), scheduler step (:849).  No per-step empty_cache().
+
+    use_cuda_graph: the noise prediction of a step (ControlNets -> kernel-(3) merge -> UNet3D -> CFG; ~5000 launches) is
+    captured once per input signature into a CUDA graph and replayed, so the step is bound by the GPU, not by Python.
+    """
 
     def __init__(self, unet: UNet3DConditionModel, controlnets: Optional[MultiControlNetResiduals], scheduler: DDIMScheduler,
-                 guidance_scale: float = 7.5, guess_mode: bool = False):
+                 guidance_scale: float = 7.5, guess_mode: bool = False, use_cuda_graph: bool = False):
         self.unet, self.controlnets, self.scheduler = unet, controlnets, scheduler
         self.guidance_scale, self.guess_mode = guidance_scale, guess_mode
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}
 
     @property
     def do_cfg(self):
         return self.guidance_scale > 1.0
 
-    @torch.no_grad()
-    def step(self, latents: torch.Tensor, t: int, prompt_embeds: torch.Tensor) -> torch.Tensor:
-        """latents [1,4,f,h,w] (fp32 or model dtype), prompt_embeds [2,L,D] = [negative, positive] when CFG."""
+    def predict_noise(self, latents: torch.Tensor, t, prompt_embeds: torch.Tensor) -> torch.Tensor:
+        """Guided noise prediction for latents [1,4,f,h,w]; `t` is an int or a 1-element int64 device tensor."""
         f = latents.shape[2]
         cfg = self.do_cfg
         model_in = torch.cat([latents] * 2) if cfg else latents                                          # :797
         down = mid = None
         if self.controlnets is not None:                                                                 # :807-819
-            single = self.guess_mode or not cfg
-            down, mid = self.controlnets(model_in[-1:] if single and cfg else model_in, t,
-                                         prompt_embeds[-1:] if single and cfg else prompt_embeds, f,
+            single = (self.guess_mode or not cfg) and cfg
+            down, mid = self.controlnets(model_in[-1:] if single else model_in, t,
+                                         prompt_embeds[-1:] if single else prompt_embeds, f,
                                          do_classifier_free_guidance=cfg, guess_mode=self.guess_mode)
         noise = self.unet(model_in, t, encoder_hidden_states=prompt_embeds, down_block_additional_residuals=down,
                           mid_block_additional_residual=mid).sample.to(latents.dtype)                   # :836-841
         if cfg:
             u, c = noise.chunk(2)
             noise = u + self.guidance_scale * (c - u)                                                    # :845-846
-        return self.scheduler.step(noise, t, latents)                                                    # :849
+        return noise
+
+    def _graphed_noise(self, latents, t: int, prompt_embeds):
+        key = (tuple(latents.shape), latents.dtype, tuple(prompt_embeds.shape), prompt_embeds.dtype, latents.device)
+        g = self._graphs.get(key)
+        if g is None:
+            s_lat, s_prompt = latents.clone(), prompt_embeds.clone()
+            s_t = torch.full((1,), int(t), dtype=torch.int64, device=latents.device)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                # warm-up: cuDNN algorithm selection, caches, workspaces
+                for _ in range(2):
+                    self.predict_noise(s_lat, s_t, s_prompt)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                s_out = self.predict_noise(s_lat, s_t, s_prompt)
+            g = self._graphs[key] = (graph, s_lat, s_t, s_prompt, s_out)
+        graph, s_lat, s_t, s_prompt, s_out = g
+        s_lat.copy_(latents, non_blocking=True)
+        if prompt_embeds.data_ptr() != s_prompt.data_ptr():
+            s_prompt.copy_(prompt_embeds, non_blocking=True)
+        s_t.fill_(int(t))
+        graph.replay()
+        return s_out
+
+    @torch.no_grad()
+    def step(self, latents: torch.Tensor, t: int, prompt_embeds: torch.Tensor) -> torch.Tensor:
+        """latents [1,4,f,h,w] (fp32 or model dtype), prompt_embeds [2,L,D] = [negative, positive] when CFG."""
+        if self.use_cuda_graph:
+            noise = self._graphed_noise(latents, t, prompt_embeds)
+        else:
+            noise = self.predict_noise(latents, t, prompt_embeds)
+        return self.scheduler.step(noise, int(t), latents)                                               # :849
 
     @torch.no_grad()
     def run(self, latents, prompt_embeds, num_inference_steps: int):

@@ -26,11 +26,16 @@ def launch_count() -> int:
     return _count
 
 
-def enable(flag: bool):
+def enable(flag: bool, backlog_ms: float = 0.0):
+    """backlog_ms > 0: first park the GPU on a spin kernel for that long so the host runs ahead and every timed span
+    measures back-to-back DEVICE time (otherwise the interval between two in-stream events also contains the host's
+    launch latency whenever the GPU out-runs Python)."""
     global _enabled, _spans, _wall
     _enabled = flag
     if flag:
         _spans = []
+        if backlog_ms > 0:
+            torch.cuda._sleep(int(backlog_ms * 1e-3 * 1.9e9))
         _wall = torch.cuda.Event(enable_timing=True)
         _wall.record()
 
@@ -84,4 +89,5 @@ def summary(peaks: dict) -> dict:
                    traffic=None, peak_source=f'{peaks["source"]} ({"sustained bf16 GEMM" if d["bound"] == "tensor" else "HBM copy"})',
                    avg_launch_us=d["us_per_launch"], launches=d["launches"], share_of_step=d["share_of_step"],
                    timing="CUDA events around each launch on the launching stream, instrumented pass after the timed region")
-    return dict(families=out, dominant=dom, own_share=own_ms / wall_ms, wall_ms=wall_ms)
+    return dict(families=out, dominant=dom, own_share=own_ms / wall_ms, wall_ms=wall_ms,
+                launches_per_step=sum(f["launches"] for f in fam.values()))

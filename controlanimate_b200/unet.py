@@ -229,6 +229,8 @@ class UNet3DConditionModel(nn.Module):
 
         res = ResidualSet.coerce(down_block_additional_residuals, mid_block_additional_residual, frames)
         if res is not None:                                                                # :567-576 (kernel 3, in place)
+            # the reference builds NEW skip tensors; the last skip aliases the mid-block input, which must stay un-added
+            skips[-1] = skips[-1].clone(memory_format=torch.preserve_format)
             res.add_into(skips, None)
 
         mb = self.mid_block                                                                # unet_blocks.py:273-280

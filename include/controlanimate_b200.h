@@ -112,7 +112,7 @@ int ca_temporal_attn_core(const void* q, const void* k, const void* v, void* o, 
  *   residual [m, n_out] row stride ldr or NULL; y [m, n_out] row stride ldy
  *   epilogue: CA_EPI_NONE n_out = n;  CA_EPI_GEGLU n_out = n/2: y = a * gelu_erf(g) where a/g are
  *   columns j and j + n/2 of the product (diffusers GEGLU chunk(2, -1))
- *   constraints: k % 16 == 0, n % 16 == 0, dtype bf16/f16 */
+ *   constraints: k % 8 == 0, n % 32 == 0 (n % 64 == 0 for GEGLU), 16-byte aligned rows, dtype bf16/f16 */
 typedef enum { CA_EPI_NONE = 0, CA_EPI_GEGLU = 1 } ca_epilogue_t;
 int ca_linear(const void* x, const void* w, const float* bias, const void* residual, void* y, long long m, int n,
               int k, long long ldx, long long ldr, long long ldy, int epilogue, int dtype, void* stream);

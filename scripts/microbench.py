@@ -1,0 +1,145 @@
+#!/usr/bin/env python
+"""BASELINE config 5: microbenchmark sweep of the hand-written kernels against the measured rooflines.
+
+frames 8-32 x channels 320/640/1280 x latents 32^2-96^2 (b=2), both memory layouts for GroupNorm.  Each timing is the
+median of `--iters` launches, every launch preceded by an L2 flush (256 MB write) and bracketed by CUDA events on the
+launching stream.  Writes one JSON document (default gpurun_out/microbench.json).
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from controlanimate_b200 import _lib as L, layers as Ly, ops  # noqa: E402
+
+
+def peaks():
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+def timeit(fn, iters, flush):
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush.fill_(1.0)
+        # park the GPU (~150 us) so that the launch below is already queued when e0 fires: the event interval then holds
+        # device time only, not the host's launch latency
+        torch.cuda._sleep(300000)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    return statistics.median(ts), min(ts)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--out", default="gpurun_out/microbench.json")
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    L.load(build_if_missing=False)
+    dev = torch.device("cuda")
+    hbm, tf, src = peaks()
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    rows = []
+    bt = torch.bfloat16
+    b = 2
+    frames = [16] if args.quick else [8, 16, 24, 32]
+    levels = [(320, 64), (640, 32), (1280, 16), (1280, 8)] if args.quick else \
+        [(320, 32), (320, 48), (320, 64), (320, 96), (640, 32), (640, 48), (1280, 16), (1280, 24), (1280, 8)]
+
+    def add(kernel, shape, us, us_min, nbytes, flops=0.0, **extra):
+        gbs = nbytes / us / 1e3
+        tfs = flops / us / 1e6
+        tensor_bound = flops > 0 and extra.pop("tensor", False)
+        r = dict(kernel=kernel, shape=shape, us=round(us, 2), us_min=round(us_min, 2), alg_bytes=nbytes, gbs=round(gbs, 1),
+                 frac_hbm=round(gbs / hbm, 4))
+        if flops:
+            r.update(tflops=round(tfs, 1), frac_tensor=round(tfs / tf, 4))
+        r["bound"] = "tensor" if tensor_bound else "hbm"
+        r.update(extra)
+        rows.append(r)
+        print(json.dumps(r), flush=True)
+
+    for f in frames:
+        for c, s in levels:
+            n = b * c * f * s * s
+            if n * 2 > 1.5e9:
+                continue
+            x = torch.randn(b, c, f, s, s, device=dev, dtype=bt)
+            xn = Ly.to_native(x)
+            g, be = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+            te = torch.randn(b, c, device=dev)
+            for name, inp in (("ncfhw", x), ("bfhwc", xn)):
+                y = torch.empty_like(inp)
+                us, mn = timeit(lambda: ops.groupnorm_silu(inp, g, be, 32, 1e-5, temb=te, out=y), args.iters, flush)
+                add("groupnorm_silu", f"b{b} c{c} f{f} {s}x{s} {name} +temb", us, mn, 2.0 * n * 2)
+            # LayerNorm + PE on tokens
+            tok = xn.permute(0, 2, 3, 4, 1).reshape(-1, c)
+            pe = torch.randn(32, c, device=dev)
+            yt = torch.empty_like(tok)
+            us, mn = timeit(lambda: ops.layernorm_pe(tok, g, be, 1e-5, pe=pe, frames=f, sites=s * s, out=yt), args.iters, flush)
+            add("layernorm_pe", f"T{tok.shape[0]} c{c} f{f}", us, mn, 2.0 * n * 2)
+            # temporal attention core on a packed QKV buffer
+            T = tok.shape[0]
+            qkv = torch.randn(T, 3 * c, device=dev, dtype=bt)
+            o = torch.empty(T, c, device=dev, dtype=bt)
+            us, mn = timeit(lambda: ops.temporal_attention_core(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], batch=b, frames=f,
+                                                                sites=s * s, heads=8, out=o), args.iters, flush)
+            add("temporal_attn_core", f"b{b} f{f} d{s * s} c{c} (hd {c // 8})", us, mn, 4.0 * T * c * 2, 4.0 * f * c * T)
+            if f == 16:
+                # the motion module's GEMMs: fused QKV, out-proj + residual, GEGLU, FF out
+                w3 = torch.randn(3 * c, c, device=dev, dtype=bt) * c ** -0.5
+                w1 = torch.randn(c, c, device=dev, dtype=bt) * c ** -0.5
+                wg = torch.randn(8 * c, c, device=dev, dtype=bt) * c ** -0.5
+                w2 = torch.randn(c, 4 * c, device=dev, dtype=bt) * (4 * c) ** -0.5
+                bias = torch.randn(8 * c, device=dev)
+                u = torch.randn(T, 4 * c, device=dev, dtype=bt)
+                for nm, fn, (m_, n_, k_) in (
+                        ("qkv", lambda: ops.linear(tok, w3), (T, 3 * c, c)),
+                        ("out+bias+res", lambda: ops.linear(tok, w1, bias[:c], residual=yt), (T, c, c)),
+                        ("geglu", lambda: ops.linear(tok, wg, bias, geglu=True), (T, 8 * c, c)),
+                        ("ff_out+res", lambda: ops.linear(u, w2, bias[:c], residual=yt), (T, c, 4 * c))):
+                    us, mn = timeit(fn, args.iters, flush)
+                    nb = (m_ * k_ + n_ * k_ + m_ * (n_ // 2 if nm == "geglu" else n_) * (2 if "res" in nm else 1)) * 2.0
+                    add("linear_tcgen05", f"{nm} m{m_} n{n_} k{k_}", us, mn, nb, 2.0 * m_ * n_ * k_, tensor=True)
+                    # cuBLAS yardstick for the same GEMM (library; not used on the product path)
+                    a_ = u if nm == "ff_out+res" else tok
+                    w_ = {"qkv": w3, "out+bias+res": w1, "geglu": wg, "ff_out+res": w2}[nm]
+                    us_c, mn_c = timeit(lambda: torch.nn.functional.linear(a_, w_), args.iters, flush)
+                    add("cublas_linear(yardstick)", f"{nm} m{m_} n{n_} k{k_}", us_c, mn_c, nb, 2.0 * m_ * n_ * k_, tensor=True)
+            del x, xn, tok, qkv, o, yt
+            torch.cuda.empty_cache()
+
+    # residual merge at config 2 / config 1 sizes (native layout, in place on skips)
+    from oracle import synth
+    for nets, (f, lat) in ((2, (16, 64)), (4, (16, 64)), (1, (8, 32))):
+        shapes = synth.residual_shapes()
+        raw = [[torch.randn(b * f, ch, lat // d, lat // d, device=dev, dtype=bt).contiguous(memory_format=torch.channels_last)
+                for ch, d in shapes] for _ in range(nets)]
+        skips = [torch.randn_like(t) for t in raw[0]]
+        sc = [[1.0] * 13 for _ in range(nets)]
+        E = sum(t.numel() for t in skips)
+        us, mn = timeit(lambda: ops.residual_merge(raw, sc, skips, frames=f, add_into_dst=True, layout=L.CA_LAYOUT_BFHWC), args.iters, flush)
+        add("residual_merge", f"{nets} nets, 13 tensors, E={E} (b{b} f{f} lat{lat}) in-place", us, mn, (nets + 2.0) * E * 2)
+        del raw, skips
+        torch.cuda.empty_cache()
+
+    os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+    json.dump(dict(peaks=dict(hbm_gbs=hbm, bf16_tflops=tf, source=src), rows=rows), open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
