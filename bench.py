@@ -231,11 +231,16 @@ def run_b200(args):
     profiler.reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    ncu_range = os.environ.get("CA_NCU_RANGE") == "1"      # `ncu --profile-from-start off`: capture only the timed steps
+    if ncu_range:
+        torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     for i in range(args.steps):
         latents = one_step(latents, i)
     e1.record()
     barrier()
+    if ncu_range:
+        torch.cuda.cudart().cudaProfilerStop()
     ms = e0.elapsed_time(e1) / args.steps
     launches = profiler.launch_count()
     clocks = sampler.stop() if rank == 0 else None

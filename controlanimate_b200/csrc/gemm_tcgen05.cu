@@ -367,11 +367,10 @@ int pick_bn(int n_cols, int cap) {  // largest multiple of 32 <= cap dividing n_
 }  // namespace
 }  // namespace ca
 
-extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, const void* w, const float* bias,
-                                                                const void* residual, void* y, long long m, int n, int k,
-                                                                long long ldx, long long ldr, long long ldy, int epilogue,
-                                                                int dtype, void* stream) {
-  using namespace ca;
+namespace ca {
+// Single-CTA (cta_group::1) implementation: kept as the A/B yardstick of gemm_pair_tcgen05.cu (CA_GEMM_IMPL=1cta).
+int linear_1cta(const void* x, const void* w, const float* bias, const void* residual, void* y, long long m, int n, int k,
+                long long ldx, long long ldr, long long ldy, int epilogue, int dtype, void* stream) {
   CA_CHECK_ARG(x && w && y, "linear: null pointer");
   CA_CHECK_ARG(dtype == CA_BF16 || dtype == CA_F16, "linear: dtype must be bf16 or f16 (tcgen05 kind::f16)");
   CA_CHECK_ARG(m >= 0 && n > 0 && k > 0, "linear: bad sizes m=%lld n=%d k=%d", m, n, k);
@@ -447,3 +446,4 @@ extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, c
   if (dtype == CA_BF16) return run(gemm_tcgen05_kernel<__nv_bfloat16>);
   return run(gemm_tcgen05_kernel<__half>);
 }
+}  // namespace ca

@@ -48,7 +48,10 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--out", default="gpurun_out/microbench.json")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default="", help="comma list of kernel families: gn,ln,attn,gemm,merge")
     args = ap.parse_args()
+    only = set(filter(None, args.only.split(",")))
+    want = lambda fam: not only or fam in only  # noqa: E731
     L.load(build_if_missing=False)
     dev = torch.device("cuda")
     hbm, tf, src = peaks()
@@ -82,7 +85,7 @@ def main():
             xn = Ly.to_native(x)
             g, be = torch.ones(c, device=dev), torch.zeros(c, device=dev)
             te = torch.randn(b, c, device=dev)
-            for name, inp in (("ncfhw", x), ("bfhwc", xn)):
+            for name, inp in (("ncfhw", x), ("bfhwc", xn)) if want("gn") else ():
                 y = torch.empty_like(inp)
                 us, mn = timeit(lambda: ops.groupnorm_silu(inp, g, be, 32, 1e-5, temb=te, out=y), args.iters, flush)
                 add("groupnorm_silu", f"b{b} c{c} f{f} {s}x{s} {name} +temb", us, mn, 2.0 * n * 2)
@@ -90,16 +93,18 @@ def main():
             tok = xn.permute(0, 2, 3, 4, 1).reshape(-1, c)
             pe = torch.randn(32, c, device=dev)
             yt = torch.empty_like(tok)
-            us, mn = timeit(lambda: ops.layernorm_pe(tok, g, be, 1e-5, pe=pe, frames=f, sites=s * s, out=yt), args.iters, flush)
-            add("layernorm_pe", f"T{tok.shape[0]} c{c} f{f}", us, mn, 2.0 * n * 2)
+            if want("ln"):
+                us, mn = timeit(lambda: ops.layernorm_pe(tok, g, be, 1e-5, pe=pe, frames=f, sites=s * s, out=yt), args.iters, flush)
+                add("layernorm_pe", f"T{tok.shape[0]} c{c} f{f}", us, mn, 2.0 * n * 2)
             # temporal attention core on a packed QKV buffer
             T = tok.shape[0]
             qkv = torch.randn(T, 3 * c, device=dev, dtype=bt)
             o = torch.empty(T, c, device=dev, dtype=bt)
-            us, mn = timeit(lambda: ops.temporal_attention_core(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], batch=b, frames=f,
-                                                                sites=s * s, heads=8, out=o), args.iters, flush)
-            add("temporal_attn_core", f"b{b} f{f} d{s * s} c{c} (hd {c // 8})", us, mn, 4.0 * T * c * 2, 4.0 * f * c * T)
-            if f == 16:
+            if want("attn"):
+                us, mn = timeit(lambda: ops.temporal_attention_core(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], batch=b, frames=f,
+                                                                    sites=s * s, heads=8, out=o), args.iters, flush)
+                add("temporal_attn_core", f"b{b} f{f} d{s * s} c{c} (hd {c // 8})", us, mn, 4.0 * T * c * 2, 4.0 * f * c * T)
+            if f == 16 and want("gemm"):
                 # the motion module's GEMMs: fused QKV, out-proj + residual, GEGLU, FF out
                 w3 = torch.randn(3 * c, c, device=dev, dtype=bt) * c ** -0.5
                 w1 = torch.randn(c, c, device=dev, dtype=bt) * c ** -0.5
@@ -108,6 +113,7 @@ def main():
                 bias = torch.randn(8 * c, device=dev)
                 u = torch.randn(T, 4 * c, device=dev, dtype=bt)
                 for nm, fn, (m_, n_, k_) in (
+                        ("proj_in", lambda: ops.linear(tok, w1, bias[:c]), (T, c, c)),
                         ("qkv", lambda: ops.linear(tok, w3), (T, 3 * c, c)),
                         ("out+bias+res", lambda: ops.linear(tok, w1, bias[:c], residual=yt), (T, c, c)),
                         ("geglu", lambda: ops.linear(tok, wg, bias, geglu=True), (T, 8 * c, c)),
@@ -117,7 +123,7 @@ def main():
                     add("linear_tcgen05", f"{nm} m{m_} n{n_} k{k_}", us, mn, nb, 2.0 * m_ * n_ * k_, tensor=True)
                     # cuBLAS yardstick for the same GEMM (library; not used on the product path)
                     a_ = u if nm == "ff_out+res" else tok
-                    w_ = {"qkv": w3, "out+bias+res": w1, "geglu": wg, "ff_out+res": w2}[nm]
+                    w_ = {"proj_in": w1, "qkv": w3, "out+bias+res": w1, "geglu": wg, "ff_out+res": w2}[nm]
                     us_c, mn_c = timeit(lambda: torch.nn.functional.linear(a_, w_), args.iters, flush)
                     add("cublas_linear(yardstick)", f"{nm} m{m_} n{n_} k{k_}", us_c, mn_c, nb, 2.0 * m_ * n_ * k_, tensor=True)
             del x, xn, tok, qkv, o, yt
@@ -125,7 +131,7 @@ def main():
 
     # residual merge at config 2 / config 1 sizes (native layout, in place on skips)
     from oracle import synth
-    for nets, (f, lat) in ((2, (16, 64)), (4, (16, 64)), (1, (8, 32))):
+    for nets, (f, lat) in ((2, (16, 64)), (4, (16, 64)), (1, (8, 32))) if want("merge") else ():
         shapes = synth.residual_shapes()
         raw = [[torch.randn(b * f, ch, lat // d, lat // d, device=dev, dtype=bt).contiguous(memory_format=torch.channels_last)
                 for ch, d in shapes] for _ in range(nets)]

@@ -209,6 +209,8 @@ def test_residual_merge_native_layout(ops, dtype):
 LINEAR_CASES = [
     # m, n, k
     (256, 64, 64), (128, 320, 320), (1000, 960, 320), (4096, 640, 640), (2048, 1280, 2560), (77, 192, 128), (300, 2560, 320),
+    # large-m cases: the CTA-pair kernel switches to its B-stationary schedule (K = 320) / many tiles per pair
+    (8000, 960, 320), (9001, 2560, 320), (19000, 320, 320), (5000, 320, 1280),
 ]
 
 
