@@ -40,8 +40,9 @@ constexpr int BM = 128;       // rows per CTA (UMMA_M = 256 per pair)
 constexpr int BK = 64;        // one 128-byte swizzle atom of 16-bit elements
 constexpr int UMMA_K = 16;
 constexpr int kAccCols = 256; // TMEM columns per accumulator stage
-constexpr int kEpiWarps = 8;  // 4 lane quarters x 2 column halves
-constexpr int kSlots = 4;     // staging slots per epilogue warp
+constexpr int kEpiParts = 4;  // epilogue warps per TMEM lane quarter (column parts of the tile)
+constexpr int kEpiWarps = 4 * kEpiParts;
+constexpr int kMaxSlots = 3;  // staging slots per epilogue warp: 3 with a residual (TMA-prefetched two boxes ahead), else 1
 constexpr int kSlotBytes = 2048;  // one 32 x 32 box of 16-bit elements
 constexpr int kResAhead = 2;  // residual boxes in flight per warp
 constexpr int kThreads = 128 + 32 * kEpiWarps;
@@ -54,8 +55,13 @@ struct PairParams {
   int geglu, has_res;
   int num_m_blocks, num_n_blocks, num_k_blocks, stages;  // m blocks of 256 rows
   int stationary;       // the B block of this pair stays in smem for the whole kernel
+  int slots;            // staging slots per epilogue warp
   long long tiles, tile_step;
   const float* bias;
+  void* y;
+  long long ldy;
+  int dbg;            // development aid (CA_GEMM_DBG): 1 = epilogue only releases TMEM, 2 = tcgen05.ld but no stores
+  long long* timing;  // CA_GEMM_TIMING=1: per-CTA cycle counters [gridDim.x][8] (development aid), else null
   uint32_t idesc, b_bytes, b_stride, stage_bytes, bres_bytes;  // b_bytes: this CTA's half tile; b_stride: 1024-aligned
 };
 
@@ -94,6 +100,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }
@@ -139,6 +153,12 @@ __device__ __forceinline__ f2 add2(f2 a, f2 b) {
 }
 __device__ __forceinline__ f2 splat(float c) { return pk(c, c); }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // a * GELU(g) for two columns, exact-erf definition (diffusers GEGLU uses F.gelu default).  erfc by Abramowitz-Stegun
 // 7.1.26 (abs err <= 1.5e-7): Phi(g) = 1/2 + copysign(1/2 - erfc(|g|/sqrt2)/2, g).  With z' = |g| * sqrt(log2(e)/2) the
 // Gaussian factor is ex2(-z'^2); the polynomial runs on packed fp32x2 (11.5 issue slots per output instead of ~32).
@@ -149,17 +169,17 @@ __device__ __forceinline__ f2 geglu2(f2 a, f2 g) {
   const f2 d = fma2(zp, splat(0.3275911f * 0.83255461115769776f), splat(1.0f));     // 1 + p |g| / sqrt2
   float d0, d1;
   upk(d, d0, d1);
-  const f2 t = pk(__frcp_rn(d0), __frcp_rn(d1));
-  f2 poly = fma2(t, splat(0.5f * 1.061405429f), splat(0.5f * -1.453152027f));       // coefficients pre-halved
-  poly = fma2(poly, t, splat(0.5f * 1.421413741f));
-  poly = fma2(poly, t, splat(0.5f * -0.284496736f));
-  poly = fma2(poly, t, splat(0.5f * 0.254829592f));
+  const f2 t = pk(rcp_approx(d0), rcp_approx(d1));
+  f2 poly = fma2(t, splat(-0.5f * 1.061405429f), splat(-0.5f * -1.453152027f));     // coefficients pre-halved, negated
+  poly = fma2(poly, t, splat(-0.5f * 1.421413741f));
+  poly = fma2(poly, t, splat(-0.5f * -0.284496736f));
+  poly = fma2(poly, t, splat(-0.5f * 0.254829592f));
   poly = mul2(poly, t);
   const f2 w = mul2(zp, zp);
   float w0, w1;
   upk(w, w0, w1);
   const f2 e = pk(exp2f(-w0), exp2f(-w1));                                          // --use_fast_math: MUFU.EX2
-  const f2 half_erf = fma2(poly, mul2(e, splat(-1.0f)), splat(0.5f));               // 1/2 - erfc/2  (>= 0)
+  const f2 half_erf = fma2(poly, e, splat(0.5f));                                   // 1/2 - erfc/2  (>= 0)
   float h0, h1;
   upk(half_erf, h0, h1);
   const f2 phi = add2(pk(copysignf(h0, g0), copysignf(h1, g1)), splat(0.5f));
@@ -179,21 +199,32 @@ __device__ __forceinline__ f2 unpack_f2(uint32_t w) {
   return pk(lo, hi);
 }
 
+// mbarrier wait that adds the cycles spent to `acc` when timing is on
+__device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, bool on, long long& acc) {
+  if (!on) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                     const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_r,
+                     const __grid_constant__ CUtensorMap map_r,
                      const PairParams p) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tmem_full[2], tmem_empty[2], bres_full;
-  __shared__ uint64_t res_full[kEpiWarps][kSlots];
+  __shared__ uint64_t res_full[kEpiWarps][kMaxSlots];
   __shared__ uint32_t tmem_base_slot;
 
   // SWIZZLE_128B tiles must start on 1024-byte boundaries (same offsets in both CTAs of the pair)
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   unsigned char* bres = smem;                        // [num_k_blocks][b_stride] when stationary
   unsigned char* ring = smem + p.bres_bytes;         // [stages][stage_bytes]: A tile (+ B half tile)
-  unsigned char* slots = ring + (size_t)p.stages * p.stage_bytes;  // [kEpiWarps][kSlots][kSlotBytes]
+  unsigned char* slots = ring + (size_t)p.stages * p.stage_bytes;  // [kEpiWarps][p.slots][kSlotBytes]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -203,16 +234,16 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&full_bar[s], 2);   // leader's arrive.expect_tx + the peer's remote arrive
+      mbar_init(&full_bar[s], 1);   // the leader's arrive.expect_tx covers the bytes of both CTAs (see producer)
       mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 2 * kEpiWarps);  // epilogue warps of both CTAs
+        mbar_init(&tmem_empty[s], 2 * kEpiWarps);  // epilogue warps of both CTAs
     }
-    mbar_init(&bres_full, 2);
+    mbar_init(&bres_full, 1);
     for (int w = 0; w < kEpiWarps; ++w)
-      for (int s = 0; s < kSlots; ++s) mbar_init(&res_full[w][s], 1);
+      for (int s = 0; s < kMaxSlots; ++s) mbar_init(&res_full[w][s], 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_pair(&tmem_base_slot, 512);
@@ -221,22 +252,30 @@ __global__ void __launch_bounds__(kThreads, 1)
   cluster_sync_all();  // barrier inits of the peer are visible before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  const bool timing = p.timing != nullptr;
+  long long t_wait_a = 0, t_wait_b = 0;
+  const long long t_begin = timing ? clock64() : 0;
   const bool active = !(p.stationary && pair >= p.tile_step);  // stationary: pairs beyond G * n_blocks have no tiles
   const int half = p.bn / 2;
 
   if (warp == 0) {
     // ===================== TMA producer (one thread per CTA) =====================
-    if (lane == 0 && active) {
-      prefetch_tensormap(&map_x);
-      prefetch_tensormap(&map_w);
+    if (active) {  // the whole warp walks the loop (convergent, warp-uniform state); one elected lane issues
+      if (lane == 0) {
+        prefetch_tensormap(&map_x);
+        prefetch_tensormap(&map_w);
+      }
       // rows of w this CTA supplies for n-block nb: plain = its half of [n0, n0+BN); GEGLU = values (rank 0) / gates (rank 1)
       auto b_row = [&](int nb) { return p.geglu ? (int)rank * (p.n / 2) + nb * half : nb * p.bn + (int)rank * half; };
       if (p.stationary) {
         const int nb = (int)(pair % p.num_n_blocks);
         const uint32_t bar = mapa_u32(&bres_full, 0);
-        if (leader) mbar_arrive_expect_tx(&bres_full, 2u * p.b_bytes * (uint32_t)p.num_k_blocks);
-        else mbar_arrive_cluster(bar);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) tma_load_2d_pair(bres + (size_t)kb * p.b_stride, &map_w, bar, kb * BK, b_row(nb));
+        if (elect_one()) {
+          if (leader) mbar_arrive_expect_tx(&bres_full, 2u * p.b_bytes * (uint32_t)p.num_k_blocks);
+          for (int kb = 0; kb < p.num_k_blocks; ++kb)
+            tma_load_2d_pair(bres + (size_t)kb * p.b_stride, &map_w, bar, kb * BK, b_row(nb));
+        }
+        __syncwarp();
       }
       const uint32_t stage_tx = kABytes + (p.stationary ? 0u : p.b_bytes);
       int stage = 0;
@@ -246,23 +285,30 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int mb = (int)(tile / p.num_n_blocks);
         const int a_row = mb * 2 * BM + (int)rank * BM;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          timed_wait(&empty_bar[stage], phase ^ 1, timing, t_wait_a);
           unsigned char* sa = ring + (size_t)stage * p.stage_bytes;
           const uint32_t bar = mapa_u32(&full_bar[stage], 0);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * stage_tx);
-          else mbar_arrive_cluster(bar);
-          tma_load_2d_pair(sa, &map_x, bar, kb * BK, a_row);
-          if (!p.stationary) tma_load_2d_pair(sa + kABytes, &map_w, bar, kb * BK, b_row(nb));
+          // Only the leader arrives (expecting the bytes of both CTAs); the peer just issues its loads.  A peer load
+          // of phase n+1 cannot land before the leader's barrier finished phase n: the peer waits on empty_bar, which
+          // the leader's MMAs signal only after consuming phase n.  (A remote release-arrive here costs a MEMBAR per
+          // k-block on the producer's critical path: 3x slower main loop, profiles/r01b.)
+          if (elect_one()) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * stage_tx);
+            tma_load_2d_pair(sa, &map_x, bar, kb * BK, a_row);
+            if (!p.stationary) tma_load_2d_pair(sa + kABytes, &map_w, bar, kb * BK, b_row(nb));
+          }
+          __syncwarp();
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
           }
         }
       }
+      if (timing && lane == 0) p.timing[blockIdx.x * 8 + 3] = t_wait_a;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread of the leader CTA) =====================
-    if (lane == 0 && leader && active) {
+    if (leader && active) {  // convergent warp; tcgen05.mma / commit by one elected lane
       if (p.stationary) {
         mbar_wait(&bres_full, 0);
         tc_fence_after();
@@ -272,56 +318,75 @@ __global__ void __launch_bounds__(kThreads, 1)
       long long it = 0;
       for (long long tile = pair; tile < p.tiles; tile += p.tile_step, ++it) {
         const int acc = (int)(it & 1);
-        mbar_wait(&tmem_empty[acc], (uint32_t)((it >> 1) & 1) ^ 1);
+        timed_wait(&tmem_empty[acc], (uint32_t)((it >> 1) & 1) ^ 1, timing, t_wait_a);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * kAccCols;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          timed_wait(&full_bar[stage], phase, timing, t_wait_b);
           tc_fence_after();
           const uint32_t sa = smem_u32(ring + (size_t)stage * p.stage_bytes);
           const uint32_t sb = p.stationary ? smem_u32(bres + (size_t)kb * p.b_stride) : sa + kABytes;
           const uint64_t adesc = make_sw128_desc(sa);
           const uint64_t bdesc = make_sw128_desc(sb);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_f16_pair(tmem_d, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), p.idesc, (kb | ks) != 0 ? 1u : 0u);
+            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+              // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
+              umma_f16_pair(tmem_d, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), p.idesc, (kb | ks) != 0 ? 1u : 0u);
+            }
+            umma_commit_pair(&empty_bar[stage]);  // frees this smem stage in both CTAs once the MMAs above have read it
+            if (kb == p.num_k_blocks - 1) umma_commit_pair(&tmem_full[acc]);
           }
-          umma_commit_pair(&empty_bar[stage]);  // frees this smem stage in both CTAs once the MMAs above have read it
-          if (kb == p.num_k_blocks - 1) umma_commit_pair(&tmem_full[acc]);
+          __syncwarp();
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
           }
         }
       }
+      if (timing && lane == 0) {
+        p.timing[blockIdx.x * 8 + 0] = clock64() - t_begin;
+        p.timing[blockIdx.x * 8 + 1] = t_wait_a;
+        p.timing[blockIdx.x * 8 + 2] = t_wait_b;
+      }
     }
   } else if (warp >= 4 && active) {
     // ===================== epilogue: TMEM -> registers -> swizzled smem slot -> TMA store =====================
-    const int ew = warp - 4, q = warp & 3, hsel = ew >> 2;
+    // warp w drains TMEM lane quarter q = w % 4 (hardware restriction) and column part (w - 4) / 4 of the tile, one
+    // 32 x 32 box at a time (two tcgen05.ld of 16 columns).  Each warp owns `nslots` 2 KB staging slots
+    // (SWIZZLE_64B: conflict-free 16-byte accesses); with a residual the slot is first filled by a TMA load issued two
+    // boxes earlier, the sum is written back in place and the slot leaves through a TMA tensor store.
+    const int ew = warp - 4, q = warp & 3, part = ew >> 2;
     const int out_cols = p.geglu ? half : p.bn;
     const int boxes = out_cols / 32;
-    const int b_begin = (boxes * hsel) / 2, b_end = (boxes * (hsel + 1)) / 2;
-    unsigned char* my_slots = slots + (size_t)ew * kSlots * kSlotBytes;
+    const int b_begin = (boxes * part) / kEpiParts, b_end = (boxes * (part + 1)) / kEpiParts;
+    const uint32_t nslots = (uint32_t)p.slots;
+    unsigned char* my_slots = slots + (size_t)ew * nslots * kSlotBytes;
     const int sw = (lane >> 1) & 3;  // SWIZZLE_64B: 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)
-    const uint32_t tmem_empty_leader[2] = {mapa_u32(&tmem_empty[0], 0), mapa_u32(&tmem_empty[1], 0)};
-    if (lane == 0) {
-      prefetch_tensormap(&map_y);
-      if (p.has_res) prefetch_tensormap(&map_r);
-    }
+    const uint32_t empty_remote0 = mapa_u32(&tmem_empty[0], 0), empty_remote1 = mapa_u32(&tmem_empty[1], 0);
+    auto release_acc = [&](int acc) {  // TMEM stage fully read by this warp (tcgen05.wait::ld done): hand it back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_cluster_relaxed(acc ? empty_remote1 : empty_remote0);
+      }
+    };
+    if (lane == 0 && p.has_res) prefetch_tensormap(&map_r);
+    T* __restrict__ y = reinterpret_cast<T*>(p.y);
     auto tile_row0 = [&](long long tile) { return (int)(tile / p.num_n_blocks) * 2 * BM + (int)rank * BM + q * 32; };
     auto tile_col0 = [&](long long tile) { return (int)(tile % p.num_n_blocks) * out_cols; };
 
     // residual prefetch cursor (lane 0 only): runs kResAhead boxes ahead of the compute cursor
     long long pf_tile = pair;
     int pf_bx = b_begin;
-    uint32_t pf_g = 0;
+    uint32_t pf_slot = 0;
     auto prefetch_one = [&]() {
       if (pf_tile >= p.tiles) return;
-      const uint32_t s = pf_g % kSlots;
-      mbar_arrive_expect_tx(&res_full[ew][s], kSlotBytes);
-      tma_load_2d(my_slots + s * kSlotBytes, &map_r, &res_full[ew][s], tile_col0(pf_tile) + pf_bx * 32, tile_row0(pf_tile));
-      ++pf_g;
+      mbar_arrive_expect_tx(&res_full[ew][pf_slot], kSlotBytes);
+      tma_load_2d(my_slots + pf_slot * kSlotBytes, &map_r, &res_full[ew][pf_slot], tile_col0(pf_tile) + pf_bx * 32,
+                  tile_row0(pf_tile));
+      if (++pf_slot == nslots) pf_slot = 0;
       if (++pf_bx == b_end) {
         pf_bx = b_begin;
         pf_tile += p.tile_step;
@@ -332,98 +397,111 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int i = 0; i < kResAhead; ++i) prefetch_one();
     }
 
-    uint32_t g = 0;  // boxes processed by this warp
+    uint32_t slot = 0, slot_phase = 0;  // staging slot of the current box; parity of its residual barrier
     long long it = 0;
     for (long long tile = pair; tile < p.tiles; tile += p.tile_step, ++it) {
       const int acc = (int)(it & 1);
       const int row0 = tile_row0(tile), n0 = tile_col0(tile);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kAccCols;
-      mbar_wait(&tmem_full[acc], (uint32_t)((it >> 1) & 1));
+      timed_wait(&tmem_full[acc], (uint32_t)((it >> 1) & 1), timing, t_wait_a);
       tc_fence_after();
-      if (b_begin == b_end) {  // nothing to drain for this warp (tile narrower than 64 columns)
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(tmem_empty_leader[acc]);
+      if (b_begin == b_end || p.dbg == 1) {  // nothing to drain for this warp (tile narrower than 128 columns)
+        release_acc(acc);
         continue;
       }
 #pragma unroll 1
-      for (int bx = b_begin; bx < b_end; ++bx, ++g) {
+      for (int bx = b_begin; bx < b_end; ++bx) {
         const int col = bx * 32;
-        const uint32_t slot = g % kSlots;
         unsigned char* buf = my_slots + slot * kSlotBytes;
-        uint32_t r[32];
-        f2 v[16];
-        tmem_ld32(taddr + col, r);
-        const int gc = n0 + col;  // global output column
-        if (p.geglu) {
-          uint32_t gt[32];
-          tmem_ld32(taddr + out_cols + col, gt);
-          tmem_ld_wait();
+        // the slot refilled below (residual of box + kResAhead) was drained kSlots - kResAhead boxes ago by this warp's
+        // own ld.shared / st.global (program order), so lane 0 may hand it to the TMA engine right away
+        if (p.has_res && lane == 0) prefetch_one();
+        bool res_ready = false;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
-            if (p.bias) {
-              ba = __ldg(reinterpret_cast<const float4*>(p.bias + gc + j));
-              bg = __ldg(reinterpret_cast<const float4*>(p.bias + p.n / 2 + gc + j));
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t r[16];
+          f2 v[8];
+          const int c16 = col + 16 * hh;
+          const int gc = n0 + c16;  // global output column
+          tmem_ld16(taddr + c16, r);
+          if (p.geglu) {
+            uint32_t gt[16];
+            tmem_ld16(taddr + out_cols + c16, gt);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+              if (p.bias) {
+                ba = __ldg(reinterpret_cast<const float4*>(p.bias + gc + j));
+                bg = __ldg(reinterpret_cast<const float4*>(p.bias + p.n / 2 + gc + j));
+              }
+              const f2 a0 = add2(pk(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), pk(ba.x, ba.y));
+              const f2 a1 = add2(pk(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), pk(ba.z, ba.w));
+              const f2 g0 = add2(pk(__uint_as_float(gt[j]), __uint_as_float(gt[j + 1])), pk(bg.x, bg.y));
+              const f2 g1 = add2(pk(__uint_as_float(gt[j + 2]), __uint_as_float(gt[j + 3])), pk(bg.z, bg.w));
+              v[j / 2] = geglu2(a0, g0);
+              v[j / 2 + 1] = geglu2(a1, g1);
             }
-            const f2 a0 = add2(pk(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), pk(ba.x, ba.y));
-            const f2 a1 = add2(pk(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), pk(ba.z, ba.w));
-            const f2 g0 = add2(pk(__uint_as_float(gt[j]), __uint_as_float(gt[j + 1])), pk(bg.x, bg.y));
-            const f2 g1 = add2(pk(__uint_as_float(gt[j + 2]), __uint_as_float(gt[j + 3])), pk(bg.z, bg.w));
-            v[j / 2] = geglu2(a0, g0);
-            v[j / 2 + 1] = geglu2(a1, g1);
-          }
-        } else {
-          tmem_ld_wait();
+          } else {
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 ba = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) ba = __ldg(reinterpret_cast<const float4*>(p.bias + gc + j));
-            v[j / 2] = add2(pk(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), pk(ba.x, ba.y));
-            v[j / 2 + 1] = add2(pk(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), pk(ba.z, ba.w));
+            for (int j = 0; j < 16; j += 4) {
+              float4 ba = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias) ba = __ldg(reinterpret_cast<const float4*>(p.bias + gc + j));
+              v[j / 2] = add2(pk(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), pk(ba.x, ba.y));
+              v[j / 2 + 1] = add2(pk(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), pk(ba.z, ba.w));
+            }
+          }
+          if (hh == 1 && bx == b_end - 1) release_acc(acc);
+          if (p.dbg == 2) {
+            if (__uint_as_float(r[0]) == 123.456f) y[0] = T(v[0].v != 0);
+            continue;
+          }
+          if (p.has_res) {
+            if (!res_ready) {
+              timed_wait(&res_full[ew][slot], slot_phase, timing, t_wait_b);
+              res_ready = true;
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const uint4 rr = *reinterpret_cast<const uint4*>(buf + lane * 64 + (((2 * hh + c) ^ sw) * 16));
+              v[4 * c + 0] = add2(v[4 * c + 0], unpack_f2<T>(rr.x));
+              v[4 * c + 1] = add2(v[4 * c + 1], unpack_f2<T>(rr.y));
+              v[4 * c + 2] = add2(v[4 * c + 2], unpack_f2<T>(rr.z));
+              v[4 * c + 3] = add2(v[4 * c + 3], unpack_f2<T>(rr.w));
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint4 o;
+            o.x = cvt_pack<T>(v[4 * c + 0]);
+            o.y = cvt_pack<T>(v[4 * c + 1]);
+            o.z = cvt_pack<T>(v[4 * c + 2]);
+            o.w = cvt_pack<T>(v[4 * c + 3]);
+            *reinterpret_cast<uint4*>(buf + lane * 64 + (((2 * hh + c) ^ sw) * 16)) = o;
           }
         }
-        if (bx == b_end - 1) {  // accumulator stage fully read by this warp: hand it back to the MMA issuer
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(tmem_empty_leader[acc]);
-        }
-        // slot hygiene (lane 0 issues every TMA op of this warp): the store that last read the slot refilled below
-        // (box g - 2) and the one that read `buf` (box g - 4) must be done -> at most the newest store may be pending
-        if (lane == 0) {
-          bulk_wait_read<1>();
-          if (p.has_res) prefetch_one();  // residual of box g + 2 into slot (g + 2) % 4
-        }
+        // transposed write-out: the box sits in the slot row-major (64 B rows); every st.global.v4 of the warp now covers
+        // 8 rows x 64 contiguous bytes (full 32-byte sectors) instead of 32 rows x 16 bytes
         __syncwarp();
-        if (p.has_res) {
-          mbar_wait(&res_full[ew][slot], (g / kSlots) & 1);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint4 rr = *reinterpret_cast<const uint4*>(buf + lane * 64 + ((c ^ sw) * 16));
-            v[4 * c + 0] = add2(v[4 * c + 0], unpack_f2<T>(rr.x));
-            v[4 * c + 1] = add2(v[4 * c + 1], unpack_f2<T>(rr.y));
-            v[4 * c + 2] = add2(v[4 * c + 2], unpack_f2<T>(rr.z));
-            v[4 * c + 3] = add2(v[4 * c + 3], unpack_f2<T>(rr.w));
-          }
+        for (int i = 0; i < 4; ++i) {
+          const int rr = i * 8 + (lane >> 2), cc = lane & 3;
+          const uint4 o = *reinterpret_cast<const uint4*>(buf + rr * 64 + ((cc ^ ((rr >> 1) & 3)) * 16));
+          const long long grow = (long long)row0 + rr;
+          if (grow < p.m) stg_stream(y + grow * p.ldy + n0 + col + cc * 8, o);
         }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4 o;
-          o.x = cvt_pack<T>(v[4 * c + 0]);
-          o.y = cvt_pack<T>(v[4 * c + 1]);
-          o.z = cvt_pack<T>(v[4 * c + 2]);
-          o.w = cvt_pack<T>(v[4 * c + 3]);
-          *reinterpret_cast<uint4*>(buf + lane * 64 + ((c ^ sw) * 16)) = o;
-        }
-        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy) store
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&map_y, buf, n0 + col, row0);
-          bulk_commit();
+        __syncwarp();  // all lanes have read the slot before it is refilled / rewritten
+        if (++slot == nslots) {
+          slot = 0;
+          slot_phase ^= 1;
         }
       }
     }
-    if (lane == 0) bulk_wait<0>();
+    if (timing && lane == 0 && q == 0 && part < 2) {  // part 0 and part 1 may own different numbers of boxes
+      p.timing[blockIdx.x * 8 + 4 + 2 * part] = t_wait_a;
+      p.timing[blockIdx.x * 8 + 5 + 2 * part] = t_wait_b;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -435,7 +513,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 int pick_bn(int n_cols, int cap) {  // largest multiple of 32 <= cap dividing n_cols (epilogue boxes are 32 columns wide)
-  for (int bn = cap; bn >= 32; bn -= 32)
+  for (int bn = cap / 32 * 32; bn >= 32; bn -= 32)
     if (n_cols % bn == 0) return bn;
   return 0;
 }
@@ -487,7 +565,8 @@ extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, c
   p.num_k_blocks = (k + BK - 1) / BK;
   // accumulator columns per tile: as wide as divides n (<= 256), narrower when that leaves most pairs without a tile
   {
-    int cap = 256;
+    static const int cap_env = getenv("CA_GEMM_BN") ? atoi(getenv("CA_GEMM_BN")) : 256;  // development aid
+    int cap = cap_env;
     for (;;) {
       const int bn = geglu ? 2 * pick_bn(n / 2, cap / 2) : pick_bn(n, cap);
       CA_CHECK_ARG(bn >= 32, "linear: cannot tile n=%d", n);
@@ -495,11 +574,11 @@ extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, c
       p.num_n_blocks = geglu ? (n / 2) / (bn / 2) : n / bn;
       const long long tiles = (long long)p.num_m_blocks * p.num_n_blocks;
       if (tiles * 2 > pairs || bn <= 64 || cap <= 64) break;  // enough tiles for more than half of the pairs
-      cap = bn - 32 > 64 ? bn - 32 : 64;
+      cap = bn - (geglu ? 64 : 32) > 64 ? bn - (geglu ? 64 : 32) : 64;
     }
   }
   p.tiles = (long long)p.num_m_blocks * p.num_n_blocks;
-  p.bias = bias;
+  p.bias = bias; p.y = y; p.ldy = ldy;
   p.b_bytes = (uint32_t)(p.bn / 2) * BK * 2;
   p.b_stride = (p.b_bytes + 1023) & ~1023u;
   // instruction descriptor (kind::f16): D=f32 [4,6)=1; A/B format [7,10)/[10,13): 1=bf16, 0=f16; A,B K-major (bits
@@ -507,7 +586,8 @@ extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, c
   const uint32_t fmt = dtype == CA_BF16 ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 
-  const size_t slot_bytes = (size_t)kEpiWarps * kSlots * kSlotBytes;
+  p.slots = residual ? kMaxSlots : 1;
+  const size_t slot_bytes = (size_t)kEpiWarps * p.slots * kSlotBytes;
   const size_t budget = 227 * 1024 - 1024 /*alignment*/ - 1024 /*static*/ - slot_bytes;
   // B-stationary: the pair keeps its [BN x K] block resident when that still leaves >= 4 A stages and every n-block
   // gets at least one pair
@@ -534,7 +614,7 @@ extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, c
   p.stages = stages;
   const size_t smem = (size_t)p.bres_bytes + (size_t)stages * p.stage_bytes + slot_bytes + 1024;
 
-  CUtensorMap mx, mw, my, mr;
+  CUtensorMap mx, mw, mr;
   const CUtensorMapDataType dt = dtype == CA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   {
     const uint64_t dims[2] = {(uint64_t)k, (uint64_t)m};
@@ -552,12 +632,19 @@ extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, c
   {
     const uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)m};
     const uint32_t box[2] = {32, 32};
-    const uint64_t sy[1] = {(uint64_t)ldy * 2};
-    if (!encode_tensor_map(&my, dt, 2, y, dims, sy, box, CU_TENSOR_MAP_SWIZZLE_64B)) return CA_ERR_CUDA;
     const uint64_t sr[1] = {(uint64_t)(residual ? ldr : ldy) * 2};
     if (!encode_tensor_map(&mr, dt, 2, residual ? residual : y, dims, sr, box, CU_TENSOR_MAP_SWIZZLE_64B)) return CA_ERR_CUDA;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static long long* timing_buf = nullptr;
+  static const bool timing_on = getenv("CA_GEMM_TIMING") != nullptr;
+  static const int dbg_env = getenv("CA_GEMM_DBG") ? atoi(getenv("CA_GEMM_DBG")) : 0;
+  p.dbg = dbg_env;
+  if (timing_on) {
+    if (!timing_buf) CA_CUDA(cudaMalloc(&timing_buf, 8 * 1024 * sizeof(long long)));
+    CA_CUDA(cudaMemsetAsync(timing_buf, 0, 8 * 1024 * sizeof(long long), st));
+    p.timing = timing_buf;
+  }
   auto run = [&](auto kernel) -> int {
     CA_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), 227 * 1024 - 1024));
     cudaLaunchConfig_t cfg = {};
@@ -572,7 +659,20 @@ extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, c
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CA_CUDA(cudaLaunchKernelEx(&cfg, kernel, mx, mw, my, mr, p));
+    CA_CUDA(cudaLaunchKernelEx(&cfg, kernel, mx, mw, mr, p));
+    if (timing_on) {  // development aid: synchronous, prints the mean per-CTA cycle attribution of this launch
+      static long long host[8 * 1024];
+      CA_CUDA(cudaStreamSynchronize(st));
+      CA_CUDA(cudaMemcpy(host, timing_buf, sizeof(host), cudaMemcpyDeviceToHost));
+      double s8[8] = {0}, lead = 0;
+      const int ctas = (int)(2 * grid_pairs);
+      for (int c = 0; c < ctas; ++c)
+        for (int j = 0; j < 8; ++j) s8[j] += (double)host[c * 8 + j];
+      lead = ctas / 2.0;
+      fprintf(stderr, "[ca_linear timing] m=%lld n=%d k=%d bn=%d stat=%d stages=%d tiles/pair=%.1f | mma loop %.0f clk, wait tmem_empty %.0f, wait full %.0f | "
+              "producer wait empty %.0f | epi part0 wait acc %.0f res %.0f | epi part1 wait acc %.0f res %.0f\n", m, n, k, p.bn, p.stationary, p.stages,
+              (double)p.tiles / (double)p.tile_step, s8[0] / lead, s8[1] / lead, s8[2] / lead, s8[3] / ctas, s8[4] / ctas, s8[5] / ctas, s8[6] / ctas, s8[7] / ctas);
+    }
     return CA_OK;
   };
   if (dtype == CA_BF16) return run(gemm_pair_kernel<__nv_bfloat16>);

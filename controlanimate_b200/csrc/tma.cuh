@@ -129,6 +129,10 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// relaxed flavour: no MEMBAR; enough when only TMEM / mbarrier state (no generic-proxy data) is handed over
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // 2-CTA TMA load: data lands in THIS CTA's smem, completion bytes are credited to an mbarrier given by its
 // shared::cluster address (the pair leader's barrier).
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const void* map, uint32_t bar_cluster_addr, int c0, int c1) {
