@@ -279,6 +279,20 @@ def run_b200(args):
         torch.cuda.synchronize()
         kern = profiler.summary(measured_peaks())
         profiler.enable(False)
+        # shares are of the TIMED (graph-replayed) step, not of the instrumented pass whose wall clock holds the backlog
+        for fam in kern["families"].values():
+            fam["share_of_step"] = fam["ms_total"] / ms
+        kern["dominant"]["share_of_step"] = kern["families"][kern["dominant"]["kernel"]]["share_of_step"]
+        kern["own_share"] = sum(fam["ms_total"] for fam in kern["families"].values()) / ms
+        if args.torch_profile:
+            # attribution aid (never a bench value): which aten ops the non-library, non-own kernels of one eager step come from
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
+                lat2 = loop.step(lat2, timesteps[2], d_prompt)
+                torch.cuda.synchronize()
+            with open(args.torch_profile, "w") as fh:
+                fh.write(prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=120,
+                                                                             max_name_column_width=60, max_shapes_column_width=90))
 
     if rank == 0:
         peaks = measured_peaks()
@@ -324,6 +338,7 @@ def main():
     ap.add_argument("--latent", type=int, default=LATENT)
     ap.add_argument("--cpu-frames", type=int, default=1, help="frames of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--torch-profile", default="", help="write a torch.profiler op table of one eager step to this path")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

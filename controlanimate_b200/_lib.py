@@ -23,10 +23,11 @@ SIGNATURES = {
     "ca_last_error": (C.c_char_p, []),
     "ca_device_sm": (_i, []),
     "ca_groupnorm_workspace_bytes": (_sz, [_i] * 9),
-    "ca_groupnorm_silu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "ca_groupnorm_silu": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _i, _vp, _sz, _vp]),
     "ca_residual_merge": (_i, [C.POINTER(_vp), C.POINTER(_f), C.POINTER(_vp), C.POINTER(_i), _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ca_layernorm_pe": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _f, _i, _vp]),
     "ca_temporal_attn_core": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _f, _i, _vp]),
+    "ca_bias_act_residual": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _f, _i, _i, _vp]),
     "ca_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _ll, _ll, _i, _i, _vp]),
 }
 

@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "groupnorm_team.cuh"
 
 namespace ca {
 namespace {
@@ -34,7 +35,8 @@ struct GnParams {
   void* y;
   const float* gamma;
   const float* beta;
-  const float* temb;  // [b, c] or null
+  const float* temb;  // [b, c] (row stride temb_ld) or null
+  long long temb_ld;
   int b, c, f, hw, groups, cpg;
   int per_frame, apply_silu, phase;
   float eps;
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(kNcfhwThreads, 3) gn_ncfhw_kernel(const GnPara
   const int n = min(total, v0 + p.chunk_units) - v0;
   const T* __restrict__ x = reinterpret_cast<const T*>(p.x) + base;
   T* __restrict__ y = reinterpret_cast<T*>(p.y) + base;
-  const float* temb = p.temb ? p.temb + (long long)bi * p.c + g * p.cpg : nullptr;
+  const float* temb = p.temb ? p.temb + (long long)bi * p.temb_ld + g * p.cpg : nullptr;
 
   // ---- all loads up front ----
   E raw[NV];
@@ -348,7 +350,7 @@ __global__ void __launch_bounds__(320, 2) gn_bfhwc_kernel(const GnParams p) {
   const long long base = ((long long)domain * dom_rows + r0) * C + cv * VEC;  // domains are contiguous slabs
   const T* __restrict__ x = reinterpret_cast<const T*>(p.x) + base;
   T* __restrict__ y = reinterpret_cast<T*>(p.y) + base;
-  const float* temb = p.temb ? p.temb + (long long)bi * C : nullptr;
+  const float* temb = p.temb ? p.temb + (long long)bi * p.temb_ld : nullptr;
 
   uint4 raw[NV];
 #pragma unroll
@@ -629,12 +631,14 @@ extern "C" __attribute__((visibility("default"))) size_t ca_groupnorm_workspace_
                                                                                       int dtype) {
   ca::GnPlan pl;
   if (ca::make_plan(b, c, f, h, w, groups, per_frame, layout, dtype, &pl) != CA_OK) return 0;
-  return pl.partial_bytes + pl.counter_bytes + pl.final_bytes;
+  const size_t split = pl.partial_bytes + pl.counter_bytes + pl.final_bytes;
+  const size_t team = layout == CA_LAYOUT_BFHWC ? ca::gn_team_workspace_bytes(b, c, f, h, w, groups, per_frame, dtype) : 0;
+  return split > team ? split : team;
 }
 
 extern "C" __attribute__((visibility("default"))) int ca_groupnorm_silu(const void* x, void* y, const float* gamma,
-                                                                        const float* beta, const float* temb, int b, int c,
-                                                                        int f, int h, int w, int groups, float eps,
+                                                                        const float* beta, const float* temb, long long temb_ld,
+                                                                        int b, int c, int f, int h, int w, int groups, float eps,
                                                                         int per_frame, int apply_silu, int layout, int dtype,
                                                                         void* workspace, size_t workspace_bytes, void* stream) {
   using namespace ca;
@@ -642,20 +646,26 @@ extern "C" __attribute__((visibility("default"))) int ca_groupnorm_silu(const vo
   GnPlan pl;
   int rc = make_plan(b, c, f, h, w, groups, per_frame, layout, dtype, &pl);
   if (rc != CA_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (layout == CA_LAYOUT_BFHWC) {  // native layout: persistent team kernel, one HBM read + one HBM write
+    bool handled = false;
+    rc = gn_team_launch(x, y, gamma, beta, temb, temb_ld > 0 ? temb_ld : c, b, c, f, h, w, groups, eps, per_frame, apply_silu, dtype, workspace,
+                        workspace_bytes, st, &handled);
+    if (rc != CA_OK || handled) return rc;
+  }
   CA_CHECK_ARG(pl.smem <= 200 * 1024, "groupnorm: per-CTA scratch does not fit shared memory (%zu B)", pl.smem);
   CA_CHECK_ARG(pl.vec == 1 || (aligned16(x) && aligned16(y)), "groupnorm: x/y must be 16-byte aligned");
   const size_t need = pl.partial_bytes + pl.counter_bytes + pl.final_bytes;
   CA_CHECK_ARG(need == 0 || (workspace && workspace_bytes >= need), "groupnorm: workspace too small (%zu < %zu)",
                workspace_bytes, need);
   GnParams p{};
-  p.x = x; p.y = y; p.gamma = gamma; p.beta = beta; p.temb = temb;
+  p.x = x; p.y = y; p.gamma = gamma; p.beta = beta; p.temb = temb; p.temb_ld = temb_ld > 0 ? temb_ld : c;
   p.b = b; p.c = c; p.f = f; p.hw = h * w; p.groups = groups; p.cpg = c / groups;
   p.per_frame = per_frame ? 1 : 0; p.apply_silu = apply_silu ? 1 : 0; p.eps = eps;
   p.chunks = pl.chunks; p.chunk_units = pl.chunk_units; p.k = pl.k;
   p.counters = reinterpret_cast<unsigned int*>(workspace);
   p.partials = reinterpret_cast<float2*>(reinterpret_cast<char*>(workspace) + pl.counter_bytes);
   p.finals = reinterpret_cast<float2*>(reinterpret_cast<char*>(workspace) + pl.counter_bytes + pl.partial_bytes);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return dispatch_dtype(dtype, [&](auto tag) -> int {
     using T = decltype(tag);
     if (layout == CA_LAYOUT_NCFHW) return launch_ncfhw<T>(p, pl, st);

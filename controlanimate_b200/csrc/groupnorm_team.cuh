@@ -1,0 +1,16 @@
+// Internal interface of the BFHWC team GroupNorm kernel (groupnorm_team.cu), used by ca_groupnorm_silu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace ca {
+
+// Scratch the fast path needs for this shape (0 when the shape is outside the fast path).
+size_t gn_team_workspace_bytes(int b, int c, int f, int h, int w, int groups, int per_frame, int dtype);
+
+// Launches the fast path when the shape fits; *handled says whether it did (otherwise the caller uses the split kernels).
+int gn_team_launch(const void* x, void* y, const float* gamma, const float* beta, const float* temb, long long temb_ld, int b, int c, int f,
+                   int h, int w, int groups, float eps, int per_frame, int apply_silu, int dtype, void* workspace,
+                   size_t workspace_bytes, cudaStream_t st, bool* handled);
+
+}  // namespace ca

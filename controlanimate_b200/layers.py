@@ -88,6 +88,68 @@ def group_norm(x4: torch.Tensor, norm: nn.GroupNorm, frames: int, *, per_frame: 
     return frames4(y5)
 
 
+def conv_nobias(conv: nn.Conv2d, x4: torch.Tensor) -> torch.Tensor:
+    """cuDNN convolution WITHOUT its bias: torch would add it in a separate broadcast pass; the callers fold it into the
+    next fused kernel instead (GroupNorm's per-(b,c) shift, the residual epilogue, or ops.bias_act_residual)."""
+    return F.conv2d(x4, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+
+
+def conv_bias(conv: nn.Conv2d, x4: torch.Tensor, *, silu: bool = False, residual: Optional[torch.Tensor] = None,
+              extra_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """conv(x) + bias [-> SiLU] [+ residual]: cuDNN convolution followed by ONE in-place epilogue pass."""
+    y = _cl(conv_nobias(conv, x4))
+    if conv.out_channels % 8:
+        y = y + conv.bias.to(y.dtype).view(1, -1, 1, 1) if conv.bias is not None else y
+        y = F.silu(y) if silu else y
+        return y if residual is None else y + residual
+    bias = sum_f32(conv.bias, extra_bias) if extra_bias is not None else f32(conv.bias)
+    return ops.bias_act_residual(y, bias, residual, silu=silu, inplace=True)
+
+
+class _BiasSum:
+    """fp32 sum of small parameter vectors, cached until one of them changes."""
+    cache = {}
+
+
+def sum_f32(*ps: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    ps = [p for p in ps if p is not None]
+    if not ps:
+        return None
+    key = tuple((id(p), p._version, p.data_ptr(), p.device) for p in ps)
+    hit = _BiasSum.cache.get(key[0][0])
+    if hit is None or hit[0] != key:
+        total = ps[0].detach().float()
+        for p in ps[1:]:
+            total = total + p.detach().float()
+        hit = (key, total.contiguous())
+        _BiasSum.cache[key[0][0]] = hit
+    return hit[1]
+
+
+class TembBank:
+    """All time_emb_proj layers of a model evaluated as ONE GEMM per forward (they share the input silu(temb)):
+    returns, per resnet, the [b, C_out] fp32 shift GroupNorm-2 adds (projection + its bias + conv1's bias) as row-strided
+    views of one [b, sum C_out] buffer.  Replaces ~4 tiny launches per resnet (resnet.py:196-200)."""
+
+    def __init__(self):
+        self._key = None
+
+    def shifts(self, resnets, temb: torch.Tensor):
+        key = tuple((r.time_emb_proj.weight._version, r.time_emb_proj.weight.data_ptr(), r.time_emb_proj.bias._version,
+                     r.conv1.bias._version, r.conv1.bias.data_ptr()) for r in resnets)
+        if key != self._key:
+            self._w = torch.cat([r.time_emb_proj.weight.detach() for r in resnets], dim=0).contiguous()
+            self._b = torch.cat([r.time_emb_proj.bias.detach().float() + r.conv1.bias.detach().float() for r in resnets])
+            self._tb = torch.cat([r.time_emb_proj.bias.detach() for r in resnets])
+            self._cb = torch.cat([r.conv1.bias.detach().float() for r in resnets])
+            self._splits = [r.out_channels for r in resnets]
+            self._key = key
+        # same rounding points as the per-layer evaluation: the projection (with its bias) is produced in the model
+        # dtype, then widened; conv1's bias is added in fp32
+        proj = F.linear(F.silu(temb), self._w, self._tb).float() + self._cb
+        return list(proj.split(self._splits, dim=1))
+
+
 class _FusedWeights:
     """Concatenated projection weights (to_q|to_k|to_v -> one [3C, C] GEMM), rebuilt if a source changes."""
 
@@ -337,18 +399,36 @@ class B200ResnetBlock3D(nn.Module):
         use_in_shortcut = in_channels != out_channels if use_in_shortcut is None else use_in_shortcut
         self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1) if use_in_shortcut else None
 
-    def native(self, x4: torch.Tensor, temb: Optional[torch.Tensor], frames: int) -> torch.Tensor:
-        h = group_norm(x4, self.norm1, frames, per_frame=self.per_frame, silu=True)        # resnet.py:191-192
-        h = self.conv1(h)                                                                  # :194
+    def temb_shift(self, temb: Optional[torch.Tensor], batch: int) -> Optional[torch.Tensor]:
+        """[b, C] fp32 shift GroupNorm-2 adds before its statistics: time_emb_proj(silu(temb)) (resnet.py:196-200) plus
+        conv1's bias, which is constant over (f, h, w) exactly like the time embedding and therefore folds into it."""
         t = None
         if temb is not None and self.time_emb_proj is not None:
-            t = self.time_emb_proj(F.silu(temb)).float()                                   # :196-197 ([b, C], tiny)
+            t = self.time_emb_proj(F.silu(temb)).float()
+        if self.conv1.bias is not None:
+            b1 = f32(self.conv1.bias)
+            t = b1.unsqueeze(0).expand(batch, -1).contiguous() if t is None else t + b1
+        return t
+
+    def native(self, x4: torch.Tensor, temb: Optional[torch.Tensor], frames: int,
+               shift: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x4 channels_last [(b f), C, h, w].  `shift` = precomputed temb_shift (UNet batches all of them in one GEMM)."""
+        x4 = _cl(x4)
+        h = group_norm(x4, self.norm1, frames, per_frame=self.per_frame, silu=True)        # resnet.py:191-192
+        h = conv_nobias(self.conv1, h)                                                     # :194 (bias -> shift)
+        t = self.temb_shift(temb, x4.shape[0] // frames) if shift is None else shift
         h = group_norm(h, self.norm2, frames, per_frame=self.per_frame, silu=True, temb=t)  # :199-208 fused
-        h = self.conv2(h)                                                                  # :211
+        h = _cl(conv_nobias(self.conv2, h))                                                # :211 (bias -> epilogue)
+        inv = 1.0 / self.output_scale_factor
+        if self.conv_shortcut is not None and inv == 1.0 and self.in_channels % 8 == 0:
+            # 1x1 shortcut == token GEMM whose epilogue adds both biases and conv2's output   :213-216
+            n, _, hh, ww = x4.shape
+            w2 = self.conv_shortcut.weight.reshape(self.out_channels, self.in_channels)
+            y = ops.linear(tokens(x4), w2, sum_f32(self.conv_shortcut.bias, self.conv2.bias), residual=tokens(h))
+            return from_tokens(y, n, hh, ww)
         if self.conv_shortcut is not None:
-            x4 = self.conv_shortcut(x4)                                                    # :213-214
-        out = x4 + h
-        return out if self.output_scale_factor == 1.0 else out / self.output_scale_factor
+            x4 = conv_bias(self.conv_shortcut, x4)
+        return ops.bias_act_residual(h, f32(self.conv2.bias), x4, scale=inv, inplace=True)
 
     def forward(self, input_tensor, temb):
         native_in = ops.video_layout(input_tensor) == L.CA_LAYOUT_BFHWC

@@ -82,14 +82,18 @@ def groupnorm_silu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, gro
     y = torch.empty_like(x) if out is None else out  # empty_like preserves the (dense) strides
     if y.shape != x.shape or y.stride() != x.stride() or y.dtype != x.dtype:
         raise ValueError("out must match x in shape, strides and dtype")
-    g32, b32, t32 = _f32(gamma), _f32(beta), _f32(temb)
+    g32, b32 = _f32(gamma), _f32(beta)
+    t32 = temb
+    if t32 is not None and (t32.dtype != torch.float32 or t32.dim() != 2 or t32.stride(1) != 1):
+        t32 = t32.detach().float().contiguous()   # row-strided fp32 [b, c] views are passed through as they are
     if g32.numel() != c or b32.numel() != c or (t32 is not None and tuple(t32.shape) != (b, c)):
         raise ValueError("gamma/beta must be [c] and temb [b, c]")
     lib = L.load()
     nws = lib.ca_groupnorm_workspace_bytes(b, c, f, h, w, groups, int(per_frame), layout, _dt(x))
     ws = _workspace(nws, x.device)
     with P.span("groupnorm_silu", 1, 2.0 * x.numel() * x.element_size()):
-        L.check(lib.ca_groupnorm_silu(x.data_ptr(), y.data_ptr(), g32.data_ptr(), b32.data_ptr(), _ptr(t32), b, c, f, h, w,
+        L.check(lib.ca_groupnorm_silu(x.data_ptr(), y.data_ptr(), g32.data_ptr(), b32.data_ptr(), _ptr(t32),
+                                      0 if t32 is None else t32.stride(0), b, c, f, h, w,
                                       groups, float(eps), int(per_frame), int(silu), layout, _dt(x), _ptr(ws),
                                       0 if ws is None else ws.numel(), _stream()), "ca_groupnorm_silu")
     return y
@@ -201,6 +205,35 @@ def residual_merge(per_net: Sequence[Sequence[torch.Tensor]], scales: Sequence[S
     with P.span("residual_merge", 1, float(nbytes)):
         L.check(L.load().ca_residual_merge(res_ptrs, sc, dst_ptrs, chw, n_nets, n_res, b_res, b_dst, frames, int(add_into_dst),
                                            layout, _DTYPES[dtype], _stream()), "ca_residual_merge")
+
+
+def _rows_view(t: torch.Tensor, what: str) -> Tuple[int, int]:
+    """(rows, c) of a channels_last 4-D [(b f), c, h, w] activation or a dense [rows, c] token matrix."""
+    if t.dim() == 4:
+        if not t.permute(0, 2, 3, 1).is_contiguous():
+            raise ValueError(f"{what} must be channels_last")
+        return t.shape[0] * t.shape[2] * t.shape[3], t.shape[1]
+    if t.dim() == 2 and t.is_contiguous():
+        return t.shape[0], t.shape[1]
+    raise ValueError(f"{what} must be a channels_last 4-D activation or a contiguous [rows, c] matrix")
+
+
+def bias_act_residual(x: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, *,
+                      silu: bool = False, scale: float = 1.0, inplace: bool = False) -> torch.Tensor:
+    """y = (act(x + bias[c]) + residual) * scale on channels-last rows (convolution epilogue, ca_bias_act_residual)."""
+    _cuda(x, bias, residual)
+    rows, c = _rows_view(x, "x")
+    if residual is not None and (residual.shape != x.shape or residual.dtype != x.dtype or _rows_view(residual, "residual") != (rows, c)):
+        raise ValueError("residual must match x in shape, dtype and layout")
+    b32 = _f32(bias)
+    if b32 is not None and b32.numel() != c:
+        raise ValueError("bias must be [c]")
+    y = x if inplace else torch.empty_like(x)
+    nbytes = x.numel() * x.element_size() * (3 if residual is not None else 2)
+    with P.span("bias_act_residual", 1, float(nbytes)):
+        L.check(L.load().ca_bias_act_residual(x.data_ptr(), _ptr(b32), _ptr(residual), y.data_ptr(), rows, c, float(scale),
+                                              int(silu), _dt(x), _stream()), "ca_bias_act_residual")
+    return y
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, residual: Optional[torch.Tensor] = None,

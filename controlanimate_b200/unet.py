@@ -82,8 +82,8 @@ class _Block(nn.Module):
         if up is not None:
             self.upsamplers = nn.ModuleList([up])
 
-    def layer(self, j, x, temb, frames, ctx, ctx_map):
-        x = self.resnets[j].native(x, temb, frames)
+    def layer(self, j, x, temb, frames, ctx, ctx_map, shift=None):
+        x = self.resnets[j].native(x, temb, frames, shift)
         if self.has_cross_attention:
             x = self.attentions[j].native(x, frames, ctx, ctx_map)
         if self.motion_modules is not None and self.motion_modules[j] is not None:
@@ -165,6 +165,11 @@ class UNet3DConditionModel(nn.Module):
         self.conv_norm_out = Ly.InflatedGroupNormParams(norm_num_groups, boc[0], eps=norm_eps)
         self.conv_act = nn.SiLU()
         self.conv_out = nn.Conv2d(boc[0], out_channels, 3, padding=1)
+        self._temb_bank = Ly.TembBank()
+
+    def _resnets_in_order(self):
+        rs = [r for blk in self.down_blocks for r in blk.resnets] + list(self.mid_block.resnets)
+        return rs + [r for blk in self.up_blocks for r in blk.resnets]
 
     # ---- processor protocol (unet.py:320-382) ------------------------------------------------------------
     @property
@@ -215,16 +220,18 @@ class UNet3DConditionModel(nn.Module):
         timesteps = timestep.reshape(-1).to(sample.device).expand(b)
         emb = self.time_embedding(self.time_proj(timesteps).to(dtype), timestep_cond)      # :526-534 (computed once)
 
+        shifts = iter(self._temb_bank.shifts(self._resnets_in_order(), emb))               # resnet.py:196-200, batched
+
         ctx = encoder_hidden_states.to(dtype)
         x = Ly.frames4(Ly.to_native(sample.to(dtype)))
-        x = self.conv_in(x)                                                                # :547
+        x = Ly.conv_bias(self.conv_in, x)                                                  # :547
         skips = [x]
         for blk in self.down_blocks:                                                       # :551-562
             for j in range(len(blk.resnets)):
-                x = blk.layer(j, x, emb, frames, ctx, None)
+                x = blk.layer(j, x, emb, frames, ctx, None, next(shifts))
                 skips.append(x)
             if hasattr(blk, "downsamplers"):
-                x = blk.downsamplers[0].conv(x)
+                x = Ly.conv_bias(blk.downsamplers[0].conv, x)
                 skips.append(x)
 
         res = ResidualSet.coerce(down_block_additional_residuals, mid_block_additional_residual, frames)
@@ -234,11 +241,11 @@ class UNet3DConditionModel(nn.Module):
             res.add_into(skips, None)
 
         mb = self.mid_block                                                                # unet_blocks.py:273-280
-        x = mb.resnets[0].native(x, emb, frames)
+        x = mb.resnets[0].native(x, emb, frames, next(shifts))
         x = mb.attentions[0].native(x, frames, ctx, None)
         if mb.motion_modules[0] is not None:
             x = mb.motion_modules[0].native(x, frames)
-        x = mb.resnets[1].native(x, emb, frames)
+        x = mb.resnets[1].native(x, emb, frames, next(shifts))
         if res is not None:                                                                # :584-585
             x = Ly._cl(x)
             res.add_into(None, x)
@@ -248,13 +255,13 @@ class UNet3DConditionModel(nn.Module):
             rs, skips = skips[-n:], skips[:-n]
             for j in range(n):
                 x = torch.cat([x, rs.pop()], dim=1)
-                x = blk.layer(j, x, emb, frames, ctx, None)
+                x = blk.layer(j, x, emb, frames, ctx, None, next(shifts))
             if hasattr(blk, "upsamplers"):
                 if forward_upsample_size:
                     x = F.interpolate(x, size=tuple(skips[-1].shape[-2:]), mode="nearest")
                 else:
                     x = F.interpolate(x, scale_factor=2.0, mode="nearest")                 # resnet.py:63-66
-                x = blk.upsamplers[0].conv(x)
+                x = Ly.conv_bias(blk.upsamplers[0].conv, x)
 
         x = Ly.group_norm(x, self.conv_norm_out, frames, per_frame=self.per_frame, silu=True)  # :614-615
         x = self.conv_out(x)                                                               # :616
@@ -314,6 +321,7 @@ class ControlNetModel(nn.Module):
         c = boc[-1]
         self.mid_block = _Block([resnet(c, c), resnet(c, c)], [xf(c)], None)
         self.controlnet_mid_block = nn.Conv2d(c, c, 1)
+        self._temb_bank = Ly.TembBank()
 
     @staticmethod
     def _zero_conv(conv: nn.Conv2d, x4: torch.Tensor) -> torch.Tensor:
@@ -330,26 +338,29 @@ class ControlNetModel(nn.Module):
         ctx = encoder_hidden_states.to(dtype)
         if ctx_map is None and ctx.shape[0] != n:
             raise ValueError("encoder_hidden_states must have one row per frame, or pass ctx_map")
-        x = self.conv_in(Ly._cl(sample.to(dtype)))
+        resnets = [r for blk in self.down_blocks for r in blk.resnets] + list(self.mid_block.resnets)
+        shifts = iter(self._temb_bank.shifts(resnets, emb))
         ce = self.controlnet_cond_embedding
-        c = F.silu(ce.conv_in(Ly._cl(controlnet_cond.to(dtype))))
+        c = Ly.conv_bias(ce.conv_in, Ly._cl(controlnet_cond.to(dtype)), silu=True)         # conv -> +bias -> SiLU: one epilogue
         for blk in ce.blocks:
-            c = F.silu(blk(c))
-        x = x + ce.conv_out(c)
+            c = Ly.conv_bias(blk, c, silu=True)
+        # conv_in(sample) + conv_out(c): both biases and the sum in one epilogue pass
+        x = Ly.conv_bias(ce.conv_out, c, residual=Ly._cl(Ly.conv_nobias(self.conv_in, Ly._cl(sample.to(dtype)))),
+                         extra_bias=self.conv_in.bias)
         frames = 1  # every frame is an independent image here: per-frame GroupNorm statistics
         # the temb rows are per frame already (n rows), so the "batch" of the video view is n
         skips = [x]
         for blk in self.down_blocks:
             for j in range(len(blk.resnets)):
-                x = blk.layer(j, x, emb, frames, ctx, ctx_map)
+                x = blk.layer(j, x, emb, frames, ctx, ctx_map, next(shifts))
                 skips.append(x)
             if hasattr(blk, "downsamplers"):
-                x = blk.downsamplers[0].conv(x)
+                x = Ly.conv_bias(blk.downsamplers[0].conv, x)
                 skips.append(x)
         mb = self.mid_block
-        x = mb.resnets[0].native(x, emb, frames)
+        x = mb.resnets[0].native(x, emb, frames, next(shifts))
         x = mb.attentions[0].native(x, frames, ctx, ctx_map)
-        x = mb.resnets[1].native(x, emb, frames)
+        x = mb.resnets[1].native(x, emb, frames, next(shifts))
         out = [self._zero_conv(z, s) for z, s in zip(self.controlnet_down_blocks, skips)]
         out.append(self._zero_conv(self.controlnet_mid_block, x))
         return out

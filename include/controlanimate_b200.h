@@ -45,16 +45,17 @@ int ca_device_sm(void);
  * 199-208) and conv_norm_out + conv_act (animatediff/models/unet.py:614-615); with apply_silu = 0
  * also the transformer-entry GroupNorms (motion_module.py:144, attention.py:131).
  *   x, y      [b,c,f,h,w] in `layout`, dtype `dtype`; y may alias x
- *   gamma,beta[c] fp32;  temb [b,c] fp32 or NULL (the projected time embedding, resnet.py:196-200)
+ *   gamma,beta[c] fp32;  temb [b,c] fp32 with row stride temb_ld (elements; 0 = c) or NULL (the projected time
+ *             embedding, resnet.py:196-200; the caller may fold conv1's bias into it)
  *   per_frame 1: statistics per (b, f, group) over (c/groups, h, w)  (use_inflated_groupnorm, v2)
  *             0: statistics per (b, group) over (c/groups, f, h, w)  (plain nn.GroupNorm, v1)
  *   workspace ca_groupnorm_workspace_bytes(...) bytes of scratch (may be NULL if that is 0)
  * ------------------------------------------------------------------------------------------- */
 size_t ca_groupnorm_workspace_bytes(int b, int c, int f, int h, int w, int groups, int per_frame, int layout,
                                     int dtype);
-int ca_groupnorm_silu(const void* x, void* y, const float* gamma, const float* beta, const float* temb, int b, int c,
-                      int f, int h, int w, int groups, float eps, int per_frame, int apply_silu, int layout,
-                      int dtype, void* workspace, size_t workspace_bytes, void* stream);
+int ca_groupnorm_silu(const void* x, void* y, const float* gamma, const float* beta, const float* temb,
+                      long long temb_ld, int b, int c, int f, int h, int w, int groups, float eps, int per_frame,
+                      int apply_silu, int layout, int dtype, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Kernel (3): single-pass Multi-ControlNet residual merge.
@@ -116,6 +117,16 @@ int ca_temporal_attn_core(const void* q, const void* k, const void* v, void* o, 
 typedef enum { CA_EPI_NONE = 0, CA_EPI_GEGLU = 1 } ca_epilogue_t;
 int ca_linear(const void* x, const void* w, const float* bias, const void* residual, void* y, long long m, int n,
               int k, long long ldx, long long ldr, long long ldy, int epilogue, int dtype, void* stream);
+
+/* Convolution epilogue on channels-last rows:  y = (act(x + bias) + residual) * scale.
+ * Replaces the broadcast bias add behind every InflatedConv3d / nn.Conv2d of the path
+ * (animatediff/models/resnet.py:12-20), the shortcut add and 1/output_scale_factor of
+ * ResnetBlock3D.forward (resnet.py:213-216) and conv+SiLU of the ControlNet conditioning embedding
+ * (diffusers 0.23.0 ControlNetConditioningEmbedding, reached from modules/controlresiduals_pipeline.py:294-302).
+ *   x, y, residual [rows, c] dense rows, dtype; y may alias x or residual; bias [c] fp32 or NULL;
+ *   residual NULL or same shape as x; act 0 = none, 1 = SiLU; c % (16 / sizeof(dtype)) == 0 */
+int ca_bias_act_residual(const void* x, const float* bias, const void* residual, void* y, long long rows, int c,
+                         float scale, int act, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

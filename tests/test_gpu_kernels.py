@@ -61,6 +61,10 @@ GN_CASES = [
     (1, 640, 2, 64, 64, 32, True, True),   # 160 KB groups -> multi-chunk domains + domain barrier
     (1, 32, 16, 64, 64, 32, False, False), # one channel per group, long domains (split launch path)
     (2, 1280, 2, 8, 8, 32, True, True),    # tiny groups
+    (2, 320, 16, 32, 32, 32, True, True),  # 32 domains x 640 KB: several domains per team (rounds > 1), team barrier
+    (1, 960, 2, 64, 64, 32, True, False),  # 7.9 MB domains, cpg = 30: teams of ~80 CTAs
+    (3, 2560, 1, 16, 16, 32, True, True),  # one row lane per CTA (c/8 = 320 channel vectors)
+    (1, 64, 40, 96, 54, 32, False, True),  # v1 statistics over 40 frames: one 26 MB domain spread over the whole grid
 ]
 
 
@@ -79,6 +83,44 @@ def test_groupnorm_silu(ops, case, layout, dtype):
                                temb=None if temb is None else temb.cuda())
         assert y.shape == x.shape
         assert relerr(y, ref) <= REL[dtype], (case, layout, dtype, silu)
+
+
+def test_groupnorm_row_strided_temb_and_determinism(ops):
+    """temb rows may be column slices of one wide [b, sum C] buffer (layers.TembBank); results are bit-reproducible."""
+    b, c, f, h, w = 2, 320, 4, 32, 32
+    x = to_layout(synth.tensor(9, "gn.ts", (b, c, f, h, w)).bfloat16(), "bfhwc")
+    gamma, beta = 1 + synth.tensor(9, "g", (c,), 0.1), synth.tensor(9, "b", (c,), 0.1)
+    wide = synth.tensor(9, "wide", (b, 3 * c)).cuda()
+    temb = wide[:, c:2 * c]
+    assert not temb.is_contiguous()
+    ref = R.groupnorm_silu(x.float().cpu(), gamma, beta, 32, 1e-5, True, temb.cpu(), True)
+    y0 = ops.groupnorm_silu(x, gamma.cuda(), beta.cuda(), 32, 1e-5, temb=temb)
+    assert relerr(y0, ref) <= 2e-3
+    for _ in range(3):
+        assert torch.equal(ops.groupnorm_silu(x, gamma.cuda(), beta.cuda(), 32, 1e-5, temb=temb), y0)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("n,c,h,w", [(3, 320, 9, 7), (2, 16, 64, 64), (1, 1280, 8, 8)])
+def test_bias_act_residual(ops, n, c, h, w, dtype):
+    """Convolution epilogue y = (act(x + bias) + residual) * scale against plain fp32 torch on the same inputs."""
+    x = synth.tensor(11, f"bar.x{n}{c}", (n, c, h, w)).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    r = synth.tensor(11, f"bar.r{n}{c}", (n, c, h, w)).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    bias = synth.tensor(11, "bar.b", (c,), 0.5)
+    xf, rf = x.float().cpu(), r.float().cpu()
+    bb = bias.view(1, -1, 1, 1)
+    assert relerr(ops.bias_act_residual(x, bias.cuda()), xf + bb) <= REL[dtype]
+    assert relerr(ops.bias_act_residual(x, bias.cuda(), silu=True), torch.nn.functional.silu(xf + bb)) <= REL[dtype]
+    assert relerr(ops.bias_act_residual(x, bias.cuda(), r, scale=0.5), (xf + bb + rf) * 0.5) <= REL[dtype]
+    assert relerr(ops.bias_act_residual(x, None, r), xf + rf) <= REL[dtype]
+    y = ops.bias_act_residual(x.clone(), bias.cuda(), r, inplace=True)
+    assert relerr(y, xf + bb + rf) <= REL[dtype]
+    t = x.permute(0, 2, 3, 1).reshape(-1, c)                       # token-matrix view of the same memory
+    assert relerr(ops.bias_act_residual(t, bias.cuda()), (xf + bb).permute(0, 2, 3, 1).reshape(-1, c)) <= REL[dtype]
+    with pytest.raises(ValueError):
+        ops.bias_act_residual(x.contiguous(), bias.cuda())          # NCHW-contiguous is not channels-last rows
+    with pytest.raises(ValueError):
+        ops.bias_act_residual(x.cpu(), bias)
 
 
 def test_groupnorm_in_place_and_errors(ops):

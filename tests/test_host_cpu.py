@@ -22,7 +22,7 @@ def test_library_exports_every_header_symbol():
         assert getattr(lib, name) is not None
     assert b"sm_100a" in lib.ca_version()
     # argument validation happens before any CUDA call -> exercisable on CPU
-    assert lib.ca_groupnorm_silu(None, None, None, None, None, 1, 32, 1, 1, 1, 32, 1e-5, 1, 1, 0, 0, None, 0, None) == 1
+    assert lib.ca_groupnorm_silu(None, None, None, None, None, 0, 1, 32, 1, 1, 1, 32, 1e-5, 1, 1, 0, 0, None, 0, None) == 1
     assert b"null pointer" in lib.ca_last_error()
     assert lib.ca_groupnorm_workspace_bytes(2, 320, 16, 64, 64, 32, 1, 0, 0) > 0        # 80 KB groups -> 2 chunks + counters
     assert lib.ca_groupnorm_workspace_bytes(2, 1280, 16, 8, 8, 32, 1, 0, 0) == 0        # 5 KB groups -> single chunk
