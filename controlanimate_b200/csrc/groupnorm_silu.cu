@@ -38,6 +38,7 @@ struct GnParams {
   const float* temb;  // [b, c] (row stride temb_ld) or null
   long long temb_ld;
   int b, c, f, hw, groups, cpg;
+  int ld;               // BFHWC: elements between consecutive token rows (== c unless a channel slab is processed)
   int per_frame, apply_silu, phase;
   float eps;
   int chunks;           // chunks per domain
@@ -347,7 +348,8 @@ __global__ void __launch_bounds__(320, 2) gn_bfhwc_kernel(const GnParams p) {
   const int nvec = C / VEC;
   const bool on = threadIdx.x < nvec * k;
   const int cv = threadIdx.x % nvec, rl = threadIdx.x / nvec;
-  const long long base = ((long long)domain * dom_rows + r0) * C + cv * VEC;  // domains are contiguous slabs
+  const long long ld = p.ld;
+  const long long base = ((long long)domain * dom_rows + r0) * ld + cv * VEC;  // domains are contiguous slabs
   const T* __restrict__ x = reinterpret_cast<const T*>(p.x) + base;
   T* __restrict__ y = reinterpret_cast<T*>(p.y) + base;
   const float* temb = p.temb ? p.temb + (long long)bi * p.temb_ld : nullptr;
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(320, 2) gn_bfhwc_kernel(const GnParams p) {
   for (int j = 0; j < NV; ++j) {
     const int r = rl + j * k;
     raw[j] = make_uint4(0u, 0u, 0u, 0u);
-    if (on && r < rows) raw[j] = ldg_stream(x + (long long)r * C);
+    if (on && r < rows) raw[j] = ldg_stream(x + (long long)r * ld);
   }
   float tv[VEC];
 #pragma unroll
@@ -468,7 +470,7 @@ __global__ void __launch_bounds__(320, 2) gn_bfhwc_kernel(const GnParams p) {
           fv[e] = p.apply_silu ? silu_f(o) : o;
         }
         vv.pack(fv);
-        stg_stream(y + (long long)r * C, vv.raw);
+        stg_stream(y + (long long)r * ld, vv.raw);
       }
     }
   }
@@ -481,6 +483,7 @@ struct GnPlan {
   int vec;          // elements per access
   int nv;           // accesses per thread (template parameter)
   int k;            // BFHWC row lanes
+  int slabs;        // BFHWC: channel slabs (whole groups each) processed by separate launches when a row is wider than a CTA
   size_t smem;
   int threads;
   size_t partial_bytes, counter_bytes, final_bytes;
@@ -503,6 +506,7 @@ int make_plan(int b, int c, int f, int h, int w, int groups, int per_frame, int 
   constexpr int kMaxNv = 8;
   pl->k = 0;
   pl->smem = 0;
+  pl->slabs = 1;
   if (layout == CA_LAYOUT_NCFHW) {
     const long long cols = per_frame ? hw : (long long)f * hw;
     CA_CHECK_ARG(cols * cpg < (1ll << 31), "groupnorm: group too large");
@@ -519,8 +523,15 @@ int make_plan(int b, int c, int f, int h, int w, int groups, int per_frame, int 
     pl->final_bytes = sizeof(float2) * pl->domains;
   } else if (layout == CA_LAYOUT_BFHWC) {
     CA_CHECK_ARG(c % vec16 == 0, "groupnorm BFHWC: c=%d must be a multiple of %d", c, vec16);
+    // a CTA holds at most 320 channel vectors of a row; wider rows are cut into slabs of whole groups (groups are
+    // independent, so each slab is the same problem with fewer channels and the full row stride)
+    int slabs = 1;
+    while (slabs <= groups && (groups % slabs != 0 || (c / slabs) % vec16 != 0 || c / slabs / vec16 > 320)) ++slabs;
+    CA_CHECK_ARG(slabs <= groups && groups / slabs <= 256, "groupnorm BFHWC: c=%d / groups=%d too large", c, groups);
+    pl->slabs = slabs;
+    c /= slabs;
+    groups /= slabs;
     const int nvec = c / vec16;
-    CA_CHECK_ARG(nvec <= 512 && groups <= 256, "groupnorm BFHWC: c=%d / groups=%d too large", c, groups);
     const long long rows = per_frame ? hw : (long long)f * hw;
     CA_CHECK_ARG(rows < (1ll << 31), "groupnorm: domain too large");
     pl->vec = vec16;
@@ -660,7 +671,7 @@ extern "C" __attribute__((visibility("default"))) int ca_groupnorm_silu(const vo
                workspace_bytes, need);
   GnParams p{};
   p.x = x; p.y = y; p.gamma = gamma; p.beta = beta; p.temb = temb; p.temb_ld = temb_ld > 0 ? temb_ld : c;
-  p.b = b; p.c = c; p.f = f; p.hw = h * w; p.groups = groups; p.cpg = c / groups;
+  p.b = b; p.c = c / pl.slabs; p.f = f; p.hw = h * w; p.groups = groups / pl.slabs; p.cpg = c / groups; p.ld = c;
   p.per_frame = per_frame ? 1 : 0; p.apply_silu = apply_silu ? 1 : 0; p.eps = eps;
   p.chunks = pl.chunks; p.chunk_units = pl.chunk_units; p.k = pl.k;
   p.counters = reinterpret_cast<unsigned int*>(workspace);
@@ -669,6 +680,18 @@ extern "C" __attribute__((visibility("default"))) int ca_groupnorm_silu(const vo
   return dispatch_dtype(dtype, [&](auto tag) -> int {
     using T = decltype(tag);
     if (layout == CA_LAYOUT_NCFHW) return launch_ncfhw<T>(p, pl, st);
-    return launch_bfhwc<T>(p, pl, st);
+    // channel slabs run back to back on the stream, so they can share the statistics workspace
+    for (int s = 0; s < pl.slabs; ++s) {
+      GnParams q = p;
+      const long long off = (long long)s * p.c;
+      q.x = reinterpret_cast<const T*>(x) + off;
+      q.y = reinterpret_cast<T*>(y) + off;
+      q.gamma = gamma + off;
+      q.beta = beta + off;
+      q.temb = temb ? temb + off : nullptr;
+      const int rc2 = launch_bfhwc<T>(q, pl, st);
+      if (rc2 != CA_OK) return rc2;
+    }
+    return CA_OK;
   });
 }
