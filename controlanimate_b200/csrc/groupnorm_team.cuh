@@ -1,4 +1,4 @@
-// Internal interface of the BFHWC team GroupNorm kernel (groupnorm_team.cu), used by ca_groupnorm_silu.
+// Internal interface of the BFHWC fast-path GroupNorm kernels (groupnorm_team.cu, groupnorm_ring.cu), used by ca_groupnorm_silu.
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -10,6 +10,12 @@ size_t gn_team_workspace_bytes(int b, int c, int f, int h, int w, int groups, in
 
 // Launches the fast path when the shape fits; *handled says whether it did (otherwise the caller uses the split kernels).
 int gn_team_launch(const void* x, void* y, const float* gamma, const float* beta, const float* temb, long long temb_ld, int b, int c, int f,
+                   int h, int w, int groups, float eps, int per_frame, int apply_silu, int dtype, void* workspace,
+                   size_t workspace_bytes, cudaStream_t st, bool* handled);
+
+// Pipelined slice-ring kernel (groupnorm_ring.cu): same contract; tried before the team kernel.
+size_t gn_ring_workspace_bytes(int b, int c, int f, int h, int w, int groups, int per_frame, int dtype);
+int gn_ring_launch(const void* x, void* y, const float* gamma, const float* beta, const float* temb, long long temb_ld, int b, int c, int f,
                    int h, int w, int groups, float eps, int per_frame, int apply_silu, int dtype, void* workspace,
                    size_t workspace_bytes, cudaStream_t st, bool* handled);
 

@@ -2,8 +2,9 @@
 """BASELINE config 5: microbenchmark sweep of the hand-written kernels against the measured rooflines.
 
 frames 8-32 x channels 320/640/1280 x latents 32^2-96^2 (b=2), both memory layouts for GroupNorm.  Each timing is the
-median of `--iters` launches, every launch preceded by an L2 flush (256 MB write) and bracketed by CUDA events on the
-launching stream.  Writes one JSON document (default gpurun_out/microbench.json).
+median of `--iters` launches, every launch preceded by an L2 flush (256 MB write, then a 256 MB read so that the timed
+kernel starts on a cold L2 WITHOUT inheriting ~126 MB of dirty lines whose write-back would be billed to it) and
+bracketed by CUDA events on the launching stream.  Writes one JSON document (default gpurun_out/microbench.json).
 """
 import argparse
 import json
@@ -31,6 +32,7 @@ def timeit(fn, iters, flush):
     ts = []
     for _ in range(iters):
         flush.fill_(1.0)
+        flush[: flush.numel() // 2].sum()
         # park the GPU (~150 us) so that the launch below is already queued when e0 fires: the event interval then holds
         # device time only, not the host's launch latency
         torch.cuda._sleep(300000)
