@@ -495,6 +495,8 @@ int pow2_at_least(long long v, int cap) {
   return p;
 }
 
+int gn_mode();
+
 int make_plan(int b, int c, int f, int h, int w, int groups, int per_frame, int layout, int dtype, GnPlan* pl) {
   CA_CHECK_ARG(b > 0 && c > 0 && f > 0 && h > 0 && w > 0 && groups > 0, "groupnorm: non-positive dimension");
   CA_CHECK_ARG(c % groups == 0, "groupnorm: c=%d not divisible by groups=%d", c, groups);
@@ -545,7 +547,9 @@ int make_plan(int b, int c, int f, int h, int w, int groups, int per_frame, int 
     pl->threads = ((nvec * k + 31) / 32) * 32;
     if (pl->threads < groups) pl->threads = ((groups + 31) / 32) * 32;
     size_t scratch = sizeof(float) * (size_t)k * c;
-    if (pl->chunks > 1 && sizeof(float2) * (size_t)pl->chunks * groups > scratch) scratch = sizeof(float2) * (size_t)pl->chunks * groups;
+    // only the single-launch (fused) mode stages the domain's chunk partials in smem; the split launches never do
+    if (pl->chunks > 1 && gn_mode() == 1 && sizeof(float2) * (size_t)pl->chunks * groups > scratch)
+      scratch = sizeof(float2) * (size_t)pl->chunks * groups;
     pl->smem = sizeof(float) * ((size_t)c + 2 * (size_t)groups) + scratch;
     pl->partial_bytes = sizeof(float2) * pl->domains * pl->chunks * groups;
     pl->final_bytes = sizeof(float2) * pl->domains * groups;

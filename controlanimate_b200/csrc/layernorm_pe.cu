@@ -12,7 +12,10 @@
 // every warp keeps two rows of 16-byte loads in flight; gamma/beta sit in shared memory; NV (16-byte
 // vectors per lane) is a template parameter so small channel counts keep the register file free for
 // occupancy (c = 320 -> NV 2, 640 -> 3, 1280 -> 5).
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace ca {
 namespace {
@@ -119,6 +122,178 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
   }
 }
 
+
+// ---- pipelined variant (16-bit storage): rows travel HBM -> smem by bulk async copies, registers hold one row only ----
+// The register-resident kernel above keeps at most two rows of loads in flight per warp and, at ~100 registers per
+// thread, 16 warps per SM: ~40 KB outstanding per SM, measured 46 % of the copy roofline at c = 320
+// (profiles/r01c_microbench_quick.json).  Here a producer warp keeps a ring of `stages` tiles (rows_per_tile consecutive
+// rows = one contiguous span, ~20 KB) in flight per CTA with cp.async.bulk + mbarriers; consumer warps read a row from
+// smem as raw 16-byte vectors, do the exact two-pass statistics in registers and stream the result out.  Bytes in flight
+// no longer depend on registers or occupancy, and there is no CTA-wide barrier in the loop.
+constexpr int kLnRingWarps = 8;    // consumer warps
+constexpr int kLnRingStagesMax = 8;
+
+struct LnRingParams {
+  const void* x;
+  void* y;
+  const float* gamma;
+  const float* beta;
+  const float* pe;
+  long long rows;
+  int c, f, d;
+  float eps;
+  int rows_per_tile, stages;
+  long long n_tiles;
+  unsigned int tile_bytes;
+};
+
+__device__ __forceinline__ void ln_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <typename T, int LPR, int NV>
+__global__ void __launch_bounds__((kLnRingWarps + 1) * 32, 2) layernorm_ring_kernel(const LnRingParams p) {
+  constexpr int VEC = 8;
+  constexpr int R = 32 / LPR;
+  extern __shared__ __align__(128) unsigned char ln_smem[];
+  __shared__ __align__(8) uint64_t full_bar[kLnRingStagesMax], empty_bar[kLnRingStagesMax];
+  const int c = p.c, nvec = c / VEC;
+  unsigned char* ring = ln_smem;
+  float* s_g = reinterpret_cast<float*>(ln_smem + (size_t)p.stages * p.tile_bytes);
+  float* s_b = s_g + c;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    s_g[i] = p.gamma[i];
+    s_b[i] = p.beta[i];
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kLnRingWarps);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row_bytes = (long long)c * (long long)sizeof(T);
+
+  if (warp == kLnRingWarps) {
+    // ===== producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const long long r0 = t * p.rows_per_tile;
+        const long long nr = min((long long)p.rows_per_tile, p.rows - r0);
+        const uint32_t total = (uint32_t)(nr * row_bytes);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], total);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.x) + r0 * row_bytes;
+        unsigned char* dst = ring + (size_t)stage * p.tile_bytes;
+        constexpr uint32_t kPiece = 8 * 1024;
+        for (uint32_t off = 0; off < total; off += kPiece) ln_bulk_load(dst + off, src + off, min(kPiece, total - off), &full_bar[stage]);
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumers: sub-warp `sub` of warp `warp` owns rows warp*R + sub (+ kLnRingWarps*R ...) of every tile =====
+  const int sub = lane / LPR, sl = lane % LPR;
+  const float inv_c = 1.0f / (float)c;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+    const long long r0 = t * p.rows_per_tile;
+    const int nr = (int)min((long long)p.rows_per_tile, p.rows - r0);
+    mbar_wait(&full_bar[stage], phase);
+    const unsigned char* tile = ring + (size_t)stage * p.tile_bytes;
+    for (int rb = warp * R; rb < nr; rb += kLnRingWarps * R) {  // warp-uniform trip count (shuffles need the full warp)
+      const int r = rb + sub;
+      const bool live = r < nr;
+      const uint4* rowv = reinterpret_cast<const uint4*>(tile + (size_t)r * row_bytes);
+      // the row lives in registers as fp32 pairs; all arithmetic is packed f32x2 (FADD2/FFMA2: half the issue slots)
+      float2 v[NV][VEC / 2];
+      float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = sl + i * LPR;
+        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+        if (live && vi < nvec) raw = rowv[vi];
+        unpack2(raw.x, v[i][0].x, v[i][0].y, T());
+        unpack2(raw.y, v[i][1].x, v[i][1].y, T());
+        unpack2(raw.z, v[i][2].x, v[i][2].y, T());
+        unpack2(raw.w, v[i][3].x, v[i][3].y, T());
+#pragma unroll
+        for (int j = 0; j < VEC / 2; ++j) sum2 = __fadd2_rn(sum2, v[i][j]);  // padding vectors are zero
+      }
+      float sum = sum2.x + sum2.y;
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum * inv_c;
+      const float2 nmean = make_float2(-mean, -mean);
+      float2 sq2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (sl + i * LPR < nvec) {  // padding vectors must not contribute (0 - mean)^2
+#pragma unroll
+          for (int j = 0; j < VEC / 2; ++j) {
+            v[i][j] = __fadd2_rn(v[i][j], nmean);  // keep the centred value: the normalise step reuses it
+            sq2 = __ffma2_rn(v[i][j], v[i][j], sq2);
+          }
+        }
+      }
+      float sq = sq2.x + sq2.y;
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      const float rstd = rsqrtf(sq * inv_c + p.eps);
+      const float2 rstd2 = make_float2(rstd, rstd);
+      if (live) {
+        const long long row = r0 + r;
+        const float* per = p.pe ? p.pe + (long long)((row / p.d) % p.f) * c : nullptr;
+        T* yr = reinterpret_cast<T*>(p.y) + row * c;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int vi = sl + i * LPR;
+          if (vi < nvec) {
+            float2 o[VEC / 2];
+#pragma unroll
+            for (int j = 0; j < VEC / 4; ++j) {
+              const float4 g4 = *reinterpret_cast<const float4*>(s_g + vi * VEC + 4 * j);
+              const float4 b4 = *reinterpret_cast<const float4*>(s_b + vi * VEC + 4 * j);
+              float2 b01 = make_float2(b4.x, b4.y), b23 = make_float2(b4.z, b4.w);
+              if (per) {
+                const float4 p4 = __ldg(reinterpret_cast<const float4*>(per + vi * VEC + 4 * j));
+                b01 = __fadd2_rn(b01, make_float2(p4.x, p4.y));
+                b23 = __fadd2_rn(b23, make_float2(p4.z, p4.w));
+              }
+              o[2 * j] = __ffma2_rn(__fmul2_rn(v[i][2 * j], rstd2), make_float2(g4.x, g4.y), b01);
+              o[2 * j + 1] = __ffma2_rn(__fmul2_rn(v[i][2 * j + 1], rstd2), make_float2(g4.z, g4.w), b23);
+            }
+            uint4 out;
+            out.x = pack2(o[0].x, o[0].y, T());
+            out.y = pack2(o[1].x, o[1].y, T());
+            out.z = pack2(o[2].x, o[2].y, T());
+            out.w = pack2(o[3].x, o[3].y, T());
+            stg_stream(yr + vi * VEC, out);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    if (++stage == p.stages) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace ca
 
@@ -139,6 +314,52 @@ extern "C" __attribute__((visibility("default"))) int ca_layernorm_pe(const void
   while (lpr < 32 && (nvec + lpr - 1) / lpr > 5) lpr <<= 1;
   const int nv = (nvec + lpr - 1) / lpr;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static const int ring_on = [] { const char* e = getenv("CA_LN_RING"); return (e && e[0] == '0') ? 0 : 1; }();
+  static const int ring_kb = [] { const char* e = getenv("CA_LN_RING_KB"); return (e && e[0]) ? atoi(e) : 20; }();
+  static const int ring_stages = [] { const char* e = getenv("CA_LN_RING_STAGES"); return (e && e[0]) ? atoi(e) : 4; }();
+  if (ring_on && dtype != CA_F32 && nv <= 5) {
+    // pipelined path: tiles of whole row groups (kLnRingWarps * 32/lpr rows), about ring_kb KB each
+    const int group = kLnRingWarps * (32 / lpr);
+    const long long row_bytes = (long long)c * 2;
+    long long rpt = ((long long)ring_kb * 1024 / row_bytes) / group * group;
+    if (rpt < group) rpt = group;
+    LnRingParams p{};
+    p.x = x; p.y = y; p.gamma = gamma; p.beta = beta; p.pe = pe; p.rows = rows; p.c = c; p.f = f; p.d = d; p.eps = eps;
+    p.rows_per_tile = (int)rpt;
+    p.stages = ring_stages < 2 ? 2 : (ring_stages > kLnRingStagesMax ? kLnRingStagesMax : ring_stages);
+    p.n_tiles = (rows + rpt - 1) / rpt;
+    p.tile_bytes = (unsigned int)(rpt * row_bytes);
+    const size_t smem_ring = (size_t)p.stages * p.tile_bytes + 2 * (size_t)c * sizeof(float);
+    if (smem_ring <= 100 * 1024) {
+      const int threads = (kLnRingWarps + 1) * 32;
+      const int rc2 = dispatch_dtype(dtype, [&](auto tag) -> int {
+        using T = decltype(tag);
+        if constexpr (sizeof(T) == 2) {
+          auto run = [&](auto kernel) -> int {
+            const void* fn = reinterpret_cast<const void*>(kernel);
+            CA_CUDA(ensure_dynamic_smem(fn, smem_ring));
+            int per_sm = 1;
+            CA_CUDA(cached_occupancy(&per_sm, fn, threads, smem_ring));
+            long long grid = (long long)sm_count() * (per_sm < 1 ? 1 : per_sm);
+            if (grid > p.n_tiles) grid = p.n_tiles;
+            kernel<<<(unsigned)grid, threads, smem_ring, st>>>(p);
+            return CA_OK;
+          };
+#define CA_LNR_CASE(L_, N_) if (lpr == L_ && nv <= N_) return run(layernorm_ring_kernel<T, L_, N_>)
+          CA_LNR_CASE(8, 1); CA_LNR_CASE(8, 2); CA_LNR_CASE(8, 3); CA_LNR_CASE(8, 5);
+          CA_LNR_CASE(16, 3); CA_LNR_CASE(16, 5);
+          CA_LNR_CASE(32, 3); CA_LNR_CASE(32, 5);
+#undef CA_LNR_CASE
+        }
+        return CA_ERR_UNSUPPORTED;
+      });
+      if (rc2 == CA_OK) {
+        CA_CUDA(cudaGetLastError());
+        return CA_OK;
+      }
+      if (rc2 != CA_ERR_UNSUPPORTED) return rc2;
+    }
+  }
   const size_t smem = 2 * (size_t)c * sizeof(float);
   const int rc = dispatch_dtype(dtype, [&](auto tag) -> int {
     using T = decltype(tag);

@@ -92,8 +92,11 @@ __device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, uint32
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
 
-// MT = ceil(f / 16) query m-tiles (1 or 2); keys are handled as 2*MT n-tiles of 8.
-template <typename T, int MT>
+// MT = ceil(f / 16) query m-tiles (1 or 2); keys are handled as 2*MT n-tiles of 8.  HD > 0 fixes head_dim (and the smem row
+// pitch) at compile time and FULLF says f == 16*MT exactly, so the loops unroll without per-tile bounds tests; r01d's
+// capture showed the generic kernel issue-bound on index arithmetic (662 warp instructions per (site, head) unit, only 22
+// of them HMMA, 64-bit div/mod per unit), not on HBM.
+template <typename T, int MT, int HD, bool FULLF>
 __global__ void __launch_bounds__(288, MT == 1 ? 2 : 1)
     temporal_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                          const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
@@ -107,7 +110,8 @@ __global__ void __launch_bounds__(288, MT == 1 ? 2 : 1)
   const int S = p.S;
   const uint32_t tile_bytes = p.tile_bytes;
   const uint32_t stage_bytes = 3 * tile_bytes;
-  const int pitch = p.hdp * 2;  // bytes per smem row
+  const int hdp = HD > 0 ? (((HD / 8) & 1) ? HD : HD + 8) : p.hdp;
+  const int pitch = hdp * 2;  // bytes per smem row
 
   // zero all of smem once: rows beyond f are read as (masked) padding and must hold finite data
   {
@@ -126,9 +130,20 @@ __global__ void __launch_bounds__(288, MT == 1 ? 2 : 1)
   __syncthreads();
 
   // contiguous range of work units for this CTA
-  const long long per = (p.units + gridDim.x - 1) / gridDim.x;
-  const long long u0 = (long long)blockIdx.x * per;
-  const long long u1 = min(p.units, u0 + per);
+  const int per = (int)((p.units + gridDim.x - 1) / gridDim.x);
+  const int u0 = (int)min(p.units, (long long)blockIdx.x * per);
+  const int u1 = (int)min(p.units, (long long)u0 + per);
+  // unit u = (bi * site_tiles + st) * heads + head, walked incrementally (no per-unit div/mod)
+  int head = u0 % p.heads, st = (u0 / p.heads) % p.site_tiles, bi = (u0 / p.heads) / p.site_tiles;
+  auto next_unit = [&]() {
+    if (++head == p.heads) {
+      head = 0;
+      if (++st == p.site_tiles) {
+        st = 0;
+        ++bi;
+      }
+    }
+  };
 
   if (warp == S) {
     // ===== TMA producer =====
@@ -138,11 +153,7 @@ __global__ void __launch_bounds__(288, MT == 1 ? 2 : 1)
       prefetch_tensormap(&map_v);
       int stage = 0;
       uint32_t phase = 0;
-      for (long long u = u0; u < u1; ++u) {
-        const int head = (int)(u % p.heads);
-        const long long r = u / p.heads;
-        const int st = (int)(r % p.site_tiles);
-        const int bi = (int)(r / p.site_tiles);
+      for (int u = u0; u < u1; ++u, next_unit()) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         unsigned char* dst = smem + stage * stage_bytes;
         mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
@@ -160,16 +171,12 @@ __global__ void __launch_bounds__(288, MT == 1 ? 2 : 1)
   if (warp > S) return;
 
   // ===== consumers: warp w owns site (tile_site0 + w) =====
-  const int f = p.f, hd = p.hd;
-  const int site_bytes = p.fpad * pitch;
+  const int f = FULLF ? 16 * MT : p.f, hd = HD > 0 ? HD : p.hd;
+  const int site_bytes = (FULLF ? 16 * MT : p.fpad) * pitch;
   const int r0 = lane >> 2, cq = (lane & 3) * 2;  // fragment row / column-pair
   int stage = 0;
   uint32_t phase = 0;
-  for (long long u = u0; u < u1; ++u) {
-    const int head = (int)(u % p.heads);
-    const long long rr = u / p.heads;
-    const int st = (int)(rr % p.site_tiles);
-    const int bi = (int)(rr / p.site_tiles);
+  for (int u = u0; u < u1; ++u, next_unit()) {
     mbar_wait(&full_bar[stage], phase);
 
     unsigned char* base = smem + stage * stage_bytes + warp * site_bytes;
@@ -185,6 +192,7 @@ __global__ void __launch_bounds__(288, MT == 1 ? 2 : 1)
         for (int j = 0; j < 4; ++j) sacc[mt][nt][j] = 0.f;
 
     const int k16 = hd >> 4;
+#pragma unroll
     for (int ks = 0; ks < k16; ++ks) {
       uint32_t a[MT][4];
 #pragma unroll
@@ -262,6 +270,7 @@ __global__ void __launch_bounds__(288, MT == 1 ? 2 : 1)
     }
 
     // ---- O = P V, 64 output columns at a time; staged into this warp's (consumed) Q tile ----
+#pragma unroll
     for (int c0 = 0; c0 < hd; c0 += 64) {
       float oacc[MT][8][4];
 #pragma unroll
@@ -355,6 +364,7 @@ extern "C" __attribute__((visibility("default"))) int ca_temporal_attn_core(cons
   CA_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "temporal_attn_core: row strides must be multiples of 8 elements");
   CA_CHECK_ARG(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), "temporal_attn_core: pointers must be 16-byte aligned");
   CA_CHECK_ARG((long long)b * f < (1ll << 31) && d < (1 << 30), "temporal_attn_core: too many rows");
+  CA_CHECK_ARG((long long)b * d * heads < (1ll << 31), "temporal_attn_core: too many (site, head) units");
 
   AttnParams p{};
   p.b = b; p.f = f; p.d = d; p.heads = heads; p.hd = head_dim;
@@ -400,6 +410,13 @@ extern "C" __attribute__((visibility("default"))) int ca_temporal_attn_core(cons
     return CA_OK;
   };
   const bool two = f > 16;
-  if (dtype == CA_BF16) return two ? run(temporal_attn_kernel<__nv_bfloat16, 2>) : run(temporal_attn_kernel<__nv_bfloat16, 1>);
-  return two ? run(temporal_attn_kernel<__half, 2>) : run(temporal_attn_kernel<__half, 1>);
+  if (dtype == CA_BF16) {
+    if (f == 16) {  // the AnimateDiff window length: head_dim 40 / 80 / 160 are the SD1.5 motion-module widths
+      if (head_dim == 40) return run(temporal_attn_kernel<__nv_bfloat16, 1, 40, true>);
+      if (head_dim == 80) return run(temporal_attn_kernel<__nv_bfloat16, 1, 80, true>);
+      if (head_dim == 160) return run(temporal_attn_kernel<__nv_bfloat16, 1, 160, true>);
+    }
+    return two ? run(temporal_attn_kernel<__nv_bfloat16, 2, 0, false>) : run(temporal_attn_kernel<__nv_bfloat16, 1, 0, false>);
+  }
+  return two ? run(temporal_attn_kernel<__half, 2, 0, false>) : run(temporal_attn_kernel<__half, 1, 0, false>);
 }
