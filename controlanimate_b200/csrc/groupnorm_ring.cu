@@ -36,13 +36,13 @@
 namespace ca {
 namespace {
 
-constexpr int kGroupThreads = 256;                        // threads of the statistics group and of the normalise group
+constexpr int kGroupThreads = 128;                        // threads of the statistics group and of the normalise group
 constexpr int kRingThreads = 2 * kGroupThreads + 32;      // + one producer warp
-constexpr int kRingCtasPerSm = 2;
-constexpr size_t kRingSmemCap = 110 * 1024;  // dynamic smem per CTA so that two CTAs (+ static + 1 KB reserved) fit one SM
+constexpr int kRingCtasPerSm = 2;            // r01d sweep: 2 CTAs/SM with 32 KB slices beat 3 CTAs/SM with 16 KB slices
+constexpr size_t kRingSmemTotal = 222 * 1024;  // per SM, shared by the resident CTAs (+ static + 1 KB reserved each)
 constexpr int kVecE = 8;                     // 16-bit elements per 16-byte vector
 constexpr int kMaxStages = 12;
-constexpr int kFoldLanes = 16;
+constexpr int kFoldLanes = 8;
 constexpr size_t kFoldBytes = sizeof(double) * 4 * kFoldLanes * 33;
 constexpr int kMaxFolders = 8;
 
@@ -53,10 +53,11 @@ struct RingParams {
   const float* beta;
   const float* temb;  // [b, c] (row stride temb_ld) or null
   long long temb_ld;
-  int c, groups, cpg, nvec, k, gl;
+  int c, groups, cpg, nvec, k, gl;         // c = full row width (row pitch); nvec, k, gl describe one channel slab
+  int slabs, cs, gs;                       // channel slabs per row (whole groups each), channels / groups per slab
   int per_frame, f;
   float eps;
-  int dom_rows, domains, slice_rows, spd;  // spd = slices per domain
+  int dom_rows, domains, slice_rows, spd;  // spd = row slices per domain
   int n_items, stages, workers, folders;
   unsigned int stage_bytes, part_floats;
   unsigned long long* partials;  // [domains][spd][groups] packed (mean, M2) of one slice; all-ones = not written yet
@@ -113,6 +114,19 @@ __device__ __forceinline__ float tanh_fast(float v) {
   return r;
 }
 
+// mbarrier wait that backs off between probes: the three roles of a CTA share the SM's issue slots, and r01d's capture
+// showed a fifth of all issued instructions were try_wait spins
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (++spins == (1u << 24)) {
+      printf("controlanimate_b200: groupnorm ring mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 __device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kGroupThreads) : "memory"); }
 
 template <typename T, bool kSilu>
@@ -127,7 +141,7 @@ __global__ void __launch_bounds__(kRingThreads, kRingCtasPerSm) gn_ring_kernel(c
   if ((int)blockIdx.x >= p.workers) {
     double(*s_fold)[kFoldLanes][33] = reinterpret_cast<double(*)[kFoldLanes][33]>(smem_raw);
     const int lane_q = tid >> 5, lane_g = tid & 31;
-    constexpr int kBatch = 4;
+    constexpr int kBatch = 8;
     for (int dom = (int)blockIdx.x - p.workers; dom < p.domains; dom += p.folders) {
       const unsigned long long* part = p.partials + (long long)dom * p.spd * p.groups;
       for (int g0 = 0; g0 < p.groups; g0 += 32) {  // slice order, double: N, sum n*m, sum n*m^2, sum M2 (deterministic)
@@ -184,10 +198,11 @@ __global__ void __launch_bounds__(kRingThreads, kRingCtasPerSm) gn_ring_kernel(c
 
   // ===================== worker CTAs =====================
   const int G = p.workers;
+  const int Cs = p.cs;  // channels of one slab: the unit a worker handles; rows keep the full pitch C
   unsigned char* ring = smem_raw;
-  float* s_part = reinterpret_cast<float*>(smem_raw + (size_t)p.stages * p.stage_bytes);  // [k][2][C]
-  float* s_ch = s_part + p.part_floats;                                                   // [2][C] (mean_c, M2_c)
-  float2* s_fin = reinterpret_cast<float2*>(s_ch + 2 * C);                                // [2][groups] (mean, rstd), double buffer
+  float* s_part = reinterpret_cast<float*>(smem_raw + (size_t)p.stages * p.stage_bytes);  // [k][2][Cs]
+  float* s_ch = s_part + p.part_floats;                                                   // [2][Cs] (mean_c, M2_c)
+  float2* s_fin = reinterpret_cast<float2*>(s_ch + 2 * Cs);                               // [2][gs] (mean, rstd), double buffer
   const int n_my = (int)blockIdx.x < p.n_items ? (p.n_items - (int)blockIdx.x + G - 1) / G : 0;
 
   if (tid == 0) {
@@ -204,22 +219,50 @@ __global__ void __launch_bounds__(kRingThreads, kRingCtasPerSm) gn_ring_kernel(c
   const bool on = gt < nvec * k;
   const int cv = gt % nvec, rl = gt / nvec;
 
+  // item i of this CTA is q = blockIdx.x + i*G = (dom*spd + sl)*slabs + slab; (dom, sl, slab), the ring stage and its
+  // phase are advanced incrementally: r01d showed the per-item integer divisions alone cost more issue slots than the
+  // arithmetic
+  int slab = (int)blockIdx.x % p.slabs, sl = ((int)blockIdx.x / p.slabs) % p.spd, dom = ((int)blockIdx.x / p.slabs) / p.spd;
+  const int d_slab = G % p.slabs, d_sl = (G / p.slabs) % p.spd, d_dom = (G / p.slabs) / p.spd;
+  int st = 0;
+  uint32_t phase = 0;
+  auto advance = [&]() {
+    slab += d_slab;
+    sl += d_sl;
+    dom += d_dom;
+    if (slab >= p.slabs) {
+      slab -= p.slabs;
+      ++sl;
+    }
+    if (sl >= p.spd) {
+      sl -= p.spd;
+      ++dom;
+    }
+    if (++st == p.stages) {
+      st = 0;
+      phase ^= 1u;
+    }
+  };
+
   if (role == 2) {
     // ---------- producer: keeps the ring full ----------
     if (gt == 0) {
-      for (int i = 0; i < n_my; ++i) {
-        const int q = blockIdx.x + i * G;
-        const int dom = q / p.spd, sl = q - dom * p.spd;
+      for (int i = 0; i < n_my; ++i, advance()) {
         const int r0 = sl * p.slice_rows;
         const int rows = min(p.slice_rows, p.dom_rows - r0);
-        const int st = i % p.stages;
-        mbar_wait(&s_empty[st], ((uint32_t)(i / p.stages) & 1u) ^ 1u);
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.x) + ((long long)dom * p.dom_rows + r0) * C * (long long)sizeof(T);
-        const uint32_t total = (uint32_t)((size_t)rows * C * sizeof(T));
+        mbar_wait_backoff(&s_empty[st], phase ^ 1u);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.x) +
+                                   (((long long)dom * p.dom_rows + r0) * C + (long long)slab * Cs) * (long long)sizeof(T);
+        const uint32_t row_b = (uint32_t)(Cs * sizeof(T));
+        const uint32_t total = (uint32_t)rows * row_b;
+        unsigned char* dst = ring + (size_t)st * p.stage_bytes;
         mbar_arrive_expect_tx(&s_full[st], total);
-        constexpr uint32_t kPiece = 8 * 1024;
-        for (uint32_t off = 0; off < total; off += kPiece)
-          bulk_load_1d(ring + (size_t)st * p.stage_bytes + off, src + off, min(kPiece, total - off), &s_full[st]);
+        if (p.slabs == 1) {  // whole rows: the slice is one contiguous span
+          constexpr uint32_t kPiece = 8 * 1024;
+          for (uint32_t off = 0; off < total; off += kPiece) bulk_load_1d(dst + off, src + off, min(kPiece, total - off), &s_full[st]);
+        } else {             // a channel slab of every row
+          for (int r = 0; r < rows; ++r) bulk_load_1d(dst + (size_t)r * row_b, src + (size_t)r * C * sizeof(T), row_b, &s_full[st]);
+        }
       }
     }
     return;
@@ -227,61 +270,66 @@ __global__ void __launch_bounds__(kRingThreads, kRingCtasPerSm) gn_ring_kernel(c
 
   if (role == 0) {
     // ---------- statistics group: never waits on another CTA ----------
-    for (int i = 0; i < n_my; ++i) {
-      const int q = blockIdx.x + i * G;
-      const int dom = q / p.spd, sl = q - dom * p.spd;
+    for (int i = 0; i < n_my; ++i, advance()) {
       const int r0 = sl * p.slice_rows;
       const int rows = min(p.slice_rows, p.dom_rows - r0);
-      const int st = i % p.stages;
       const int bi = p.per_frame ? dom / p.f : dom;
       const uint4* bufv = reinterpret_cast<const uint4*>(ring + (size_t)st * p.stage_bytes);
-      mbar_wait(&s_full[st], (uint32_t)(i / p.stages) & 1u);
+      mbar_wait_backoff(&s_full[st], phase);
 
       if (on) {
-        float x0[kVecE], s1[kVecE], s2[kVecE];
+        // sums of (x - x0) and (x - x0)^2 per channel, x0 = the slice's first row; packed f32x2 arithmetic
+        float2 nx0[kVecE / 2], s1[kVecE / 2], s2[kVecE / 2];
         {
-          Vec16<T> v0;
-          v0.raw = bufv[cv];
-          v0.unpack(x0);
+          const uint4 r0v = bufv[cv];
+          unpack2(r0v.x, nx0[0].x, nx0[0].y, T());
+          unpack2(r0v.y, nx0[1].x, nx0[1].y, T());
+          unpack2(r0v.z, nx0[2].x, nx0[2].y, T());
+          unpack2(r0v.w, nx0[3].x, nx0[3].y, T());
         }
 #pragma unroll
-        for (int e = 0; e < kVecE; ++e) s1[e] = s2[e] = 0.f;
-#pragma unroll 2
+        for (int e = 0; e < kVecE / 2; ++e) {
+          nx0[e] = make_float2(-nx0[e].x, -nx0[e].y);
+          s1[e] = s2[e] = make_float2(0.f, 0.f);
+        }
+#pragma unroll 4
         for (int r = rl; r < rows; r += k) {
-          float fv[kVecE];
-          Vec16<T> vv;
-          vv.raw = bufv[r * nvec + cv];
-          vv.unpack(fv);
+          const uint4 raw = bufv[r * nvec + cv];
+          float2 v[kVecE / 2];
+          unpack2(raw.x, v[0].x, v[0].y, T());
+          unpack2(raw.y, v[1].x, v[1].y, T());
+          unpack2(raw.z, v[2].x, v[2].y, T());
+          unpack2(raw.w, v[3].x, v[3].y, T());
 #pragma unroll
-          for (int e = 0; e < kVecE; ++e) {
-            const float d = fv[e] - x0[e];
-            s1[e] += d;
-            s2[e] = fmaf(d, d, s2[e]);
+          for (int e = 0; e < kVecE / 2; ++e) {
+            const float2 d = __fadd2_rn(v[e], nx0[e]);
+            s1[e] = __fadd2_rn(s1[e], d);
+            s2[e] = __ffma2_rn(d, d, s2[e]);
           }
         }
-        float4* d1 = reinterpret_cast<float4*>(s_part + ((size_t)rl * 2 + 0) * C + cv * kVecE);
-        float4* d2 = reinterpret_cast<float4*>(s_part + ((size_t)rl * 2 + 1) * C + cv * kVecE);
-        d1[0] = make_float4(s1[0], s1[1], s1[2], s1[3]);
-        d1[1] = make_float4(s1[4], s1[5], s1[6], s1[7]);
-        d2[0] = make_float4(s2[0], s2[1], s2[2], s2[3]);
-        d2[1] = make_float4(s2[4], s2[5], s2[6], s2[7]);
+        float4* d1 = reinterpret_cast<float4*>(s_part + ((size_t)rl * 2 + 0) * Cs + cv * kVecE);
+        float4* d2 = reinterpret_cast<float4*>(s_part + ((size_t)rl * 2 + 1) * Cs + cv * kVecE);
+        d1[0] = make_float4(s1[0].x, s1[0].y, s1[1].x, s1[1].y);
+        d1[1] = make_float4(s1[2].x, s1[2].y, s1[3].x, s1[3].y);
+        d2[0] = make_float4(s2[0].x, s2[0].y, s2[1].x, s2[1].y);
+        d2[1] = make_float4(s2[2].x, s2[2].y, s2[3].x, s2[3].y);
       }
       group_bar(1);
       // per-channel (mean, M2) of the slice: the k row lanes share the shift, so their sums just add (fixed order)
       {
         const T* row0 = reinterpret_cast<const T*>(bufv);
         const float inv_n = 1.0f / (float)rows;
-        for (int c0 = gt; c0 < C; c0 += kGroupThreads) {
+        const float* tp = p.temb ? p.temb + (long long)bi * p.temb_ld + (long long)slab * Cs : nullptr;
+        for (int c0 = gt; c0 < Cs; c0 += kGroupThreads) {
           float a1 = 0.f, a2 = 0.f;
-#pragma unroll 4
           for (int qq = 0; qq < k; ++qq) {
-            a1 += s_part[((size_t)qq * 2 + 0) * C + c0];
-            a2 += s_part[((size_t)qq * 2 + 1) * C + c0];
+            a1 += s_part[((size_t)qq * 2 + 0) * Cs + c0];
+            a2 += s_part[((size_t)qq * 2 + 1) * Cs + c0];
           }
-          const float t = p.temb ? __ldg(p.temb + (long long)bi * p.temb_ld + c0) : 0.f;
+          const float t = tp ? __ldg(tp + c0) : 0.f;
           const float dm = a1 * inv_n;
           s_ch[c0] = Traits<T>::to_f(row0[c0]) + t + dm;
-          s_ch[C + c0] = fmaxf(a2 - a1 * dm, 0.f);
+          s_ch[Cs + c0] = fmaxf(a2 - a1 * dm, 0.f);
         }
       }
       group_bar(1);
@@ -289,28 +337,30 @@ __global__ void __launch_bounds__(kRingThreads, kRingCtasPerSm) gn_ring_kernel(c
       // lane publishes the pair as one 64-bit word
       {
         const int L = p.gl;
-        for (int g0 = 0; g0 < p.groups; g0 += kGroupThreads / L) {
+        const float inv_cpg = 1.0f / (float)p.cpg;
+        for (int g0 = 0; g0 < p.gs; g0 += kGroupThreads / L) {
           const int g = g0 + gt / L, l = gt % L;
+          const float* mc = s_ch + g * p.cpg;
           float sm = 0.f, sq = 0.f;
-          if (g < p.groups)
+          if (g < p.gs)
             for (int e = l; e < p.cpg; e += L) {
-              sm += s_ch[g * p.cpg + e];
-              sq += s_ch[C + g * p.cpg + e];
+              sm += mc[e];
+              sq += mc[Cs + e];
             }
           for (int o = L >> 1; o > 0; o >>= 1) {
             sm += __shfl_xor_sync(0xffffffffu, sm, o);
             sq += __shfl_xor_sync(0xffffffffu, sq, o);
           }
-          const float gmean = sm / (float)p.cpg;
+          const float gmean = sm * inv_cpg;
           float dv = 0.f;
-          if (g < p.groups)
+          if (g < p.gs)
             for (int e = l; e < p.cpg; e += L) {
-              const float d = s_ch[g * p.cpg + e] - gmean;
+              const float d = mc[e] - gmean;
               dv = fmaf(d, d, dv);
             }
           for (int o = L >> 1; o > 0; o >>= 1) dv += __shfl_xor_sync(0xffffffffu, dv, o);
-          if (l == 0 && g < p.groups)
-            st_relaxed64(p.partials + ((long long)dom * p.spd + sl) * p.groups + g, pack_pair(gmean, fmaf((float)rows, dv, sq)));
+          if (l == 0 && g < p.gs)
+            st_relaxed64(p.partials + ((long long)dom * p.spd + sl) * p.groups + slab * p.gs + g, pack_pair(gmean, fmaf((float)rows, dv, sq)));
         }
       }
       // no trailing barrier: s_part is rewritten only after every thread passed the second barrier above, s_ch only after
@@ -326,86 +376,106 @@ __global__ void __launch_bounds__(kRingThreads, kRingCtasPerSm) gn_ring_kernel(c
 #pragma unroll
   for (int e = 0; e < kVecE; ++e) gmap |= (unsigned int)((cv * kVecE + e) / p.cpg - g_first) << (4 * e);
 
-  auto dom_of = [&](int i) { return (int)((blockIdx.x + (long long)i * G) / p.spd); };
   // (mean, rstd) of item 0's domain -> s_fin[0]
   if (n_my > 0) {
-    for (int g = gt; g < p.groups; g += kGroupThreads) {
-      const unsigned long long* src = p.finals + (long long)dom_of(0) * p.groups + g;
+    for (int g = gt; g < p.gs; g += kGroupThreads) {
+      const unsigned long long* src = p.finals + (long long)dom * p.groups + slab * p.gs + g;
       s_fin[g] = unpack_pair(wait_pair(src, ld_relaxed64(src), 1));
     }
     group_bar(2);
   }
   for (int i = 0; i < n_my; ++i) {
-    const int q = blockIdx.x + i * G;
-    const int dom = q / p.spd, sl = q - dom * p.spd;
     const int r0 = sl * p.slice_rows;
     const int rows = min(p.slice_rows, p.dom_rows - r0);
-    const int st = i % p.stages;
     const int bi = p.per_frame ? dom / p.f : dom;
     const uint4* bufv = reinterpret_cast<const uint4*>(ring + (size_t)st * p.stage_bytes);
-    const float2* fin = s_fin + (i & 1) * p.groups;
+    const float2* fin = s_fin + (i & 1) * p.gs;
+    T* yg = reinterpret_cast<T*>(p.y) + ((long long)dom * p.dom_rows + r0) * C + (long long)slab * Cs + cv * kVecE;
+    const int my_slab = slab;
+    uint64_t* full = &s_full[st];
+    uint64_t* empty = &s_empty[st];
+    const uint32_t full_phase = phase;
+    advance();  // (dom, sl, st, phase) now describe item i + 1
 
     // the next item's statistics are requested now and tested after this item's stores (the L2 round trip is hidden)
-    const bool fetch_next = i + 1 < n_my && gt < p.groups;  // groups <= kGroupThreads is checked on the host
-    const unsigned long long* nsrc = nullptr;
-    unsigned long long nval = 0;
-    if (fetch_next) {
-      nsrc = p.finals + (long long)dom_of(i + 1) * p.groups + gt;
-      nval = ld_relaxed64(nsrc);
+    const unsigned long long* nsrc[2] = {nullptr, nullptr};
+    unsigned long long nval[2] = {0ull, 0ull};
+    if (i + 1 < n_my) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {  // groups per slab <= 2 * kGroupThreads is checked on the host
+        const int g = gt + u * kGroupThreads;
+        if (g < p.gs) {
+          nsrc[u] = p.finals + (long long)dom * p.groups + slab * p.gs + g;
+          nval[u] = ld_relaxed64(nsrc[u]);
+        }
+      }
     }
 
-    mbar_wait(&s_full[st], (uint32_t)(i / p.stages) & 1u);  // completed long ago (the statistics group consumed it): visibility only
+    mbar_wait(full, full_phase);  // completed long ago (the statistics group consumed it): visibility only
     if (on) {
-      float av[kVecE], bv[kVecE];
-      {
-        const float4* g4 = reinterpret_cast<const float4*>(p.gamma + cv * kVecE);
-        const float4* b4 = reinterpret_cast<const float4*>(p.beta + cv * kVecE);
-        const float4 ga = __ldg(g4), gb = __ldg(g4 + 1), ba = __ldg(b4), bb = __ldg(b4 + 1);
-        const float gam[kVecE] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-        const float bet[kVecE] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-        float tv[kVecE] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (p.temb) {
-          const float* tp = p.temb + (long long)bi * p.temb_ld + cv * kVecE;  // row stride may be unaligned: scalar loads
+      // gamma / beta / temb of this thread's 8 channels: L1-resident after the first item (registers are too scarce at
+      // three CTAs per SM to keep them across items)
+      const long long co = (long long)my_slab * Cs + cv * kVecE;
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + co)), gb = __ldg(reinterpret_cast<const float4*>(p.gamma + co) + 1);
+      const float4 ba = __ldg(reinterpret_cast<const float4*>(p.beta + co)), bb = __ldg(reinterpret_cast<const float4*>(p.beta + co) + 1);
+      const float gam[kVecE] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+      const float bet[kVecE] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+      float tv[kVecE] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (p.temb) {
+        const float* tp = p.temb + (long long)bi * p.temb_ld + co;  // row stride may be unaligned: scalar loads
 #pragma unroll
-          for (int e = 0; e < kVecE; ++e) tv[e] = __ldg(tp + e);
-        }
-#pragma unroll
-        for (int e = 0; e < kVecE; ++e) {
-          const float2 mr = fin[g_first + (int)((gmap >> (4 * e)) & 7u)];
-          av[e] = gam[e] * mr.y;
-          bv[e] = fmaf(tv[e] - mr.x, av[e], bet[e]);
-          if constexpr (kSilu) {
-            av[e] *= 0.5f;
-            bv[e] *= 0.5f;
-          }
-        }
+        for (int e = 0; e < kVecE; ++e) tv[e] = __ldg(tp + e);
       }
-      T* yg = reinterpret_cast<T*>(p.y) + ((long long)dom * p.dom_rows + r0) * C + cv * kVecE;
-#pragma unroll 2
-      for (int r = rl; r < rows; r += k) {
-        float fv[kVecE];
-        Vec16<T> vv;
-        vv.raw = bufv[r * nvec + cv];
-        vv.unpack(fv);
+      float2 av[kVecE / 2], bv[kVecE / 2];
 #pragma unroll
-        for (int e = 0; e < kVecE; ++e) {
-          const float hh = fmaf(fv[e], av[e], bv[e]);
-          fv[e] = kSilu ? fmaf(hh, tanh_fast(hh), hh) : hh;
+      for (int e = 0; e < kVecE; e += 2) {
+        const float2 m0 = fin[g_first + (int)((gmap >> (4 * e)) & 7u)];
+        const float2 m1 = fin[g_first + (int)((gmap >> (4 * e + 4)) & 7u)];
+        float a0 = gam[e] * m0.y, a1 = gam[e + 1] * m1.y;
+        float b0 = fmaf(tv[e] - m0.x, a0, bet[e]), b1 = fmaf(tv[e + 1] - m1.x, a1, bet[e + 1]);
+        if constexpr (kSilu) {
+          a0 *= 0.5f;
+          a1 *= 0.5f;
+          b0 *= 0.5f;
+          b1 *= 0.5f;
         }
-        vv.pack(fv);
-        stg_stream(yg + (long long)r * C, vv.raw);
+        av[e / 2] = make_float2(a0, a1);
+        bv[e / 2] = make_float2(b0, b1);
+      }
+#pragma unroll 4
+      for (int r = rl; r < rows; r += k) {
+        const uint4 raw = bufv[r * nvec + cv];
+        float2 v[kVecE / 2];
+        unpack2(raw.x, v[0].x, v[0].y, T());
+        unpack2(raw.y, v[1].x, v[1].y, T());
+        unpack2(raw.z, v[2].x, v[2].y, T());
+        unpack2(raw.w, v[3].x, v[3].y, T());
+#pragma unroll
+        for (int e = 0; e < kVecE / 2; ++e) {
+          const float2 hh = __ffma2_rn(v[e], av[e], bv[e]);
+          if constexpr (kSilu) v[e] = __ffma2_rn(hh, make_float2(tanh_fast(hh.x), tanh_fast(hh.y)), hh);
+          else v[e] = hh;
+        }
+        uint4 out;
+        out.x = pack2(v[0].x, v[0].y, T());
+        out.y = pack2(v[1].x, v[1].y, T());
+        out.z = pack2(v[2].x, v[2].y, T());
+        out.w = pack2(v[3].x, v[3].y, T());
+        stg_stream(yg + (long long)r * C, out);
       }
     }
-    if (fetch_next) s_fin[((i + 1) & 1) * p.groups + gt] = unpack_pair(wait_pair(nsrc, nval, 1));
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (nsrc[u]) s_fin[((i + 1) & 1) * p.gs + gt + u * kGroupThreads] = unpack_pair(wait_pair(nsrc[u], nval[u], 1));
     group_bar(2);  // the stage is free again and the next item's (mean, rstd) are in place
-    if (gt == 0) mbar_arrive(&s_empty[st]);
+    if (gt == 0) mbar_arrive(empty);
   }
 }
 
 struct RingPlan {
-  int domains, dom_rows, nvec, k, slice_rows, spd, n_items, stages, workers, folders;
+  int domains, dom_rows, slabs, cs, gs, nvec, k, slice_rows, spd, n_items, stages, workers, folders;
   unsigned int stage_bytes, part_floats;
-  size_t smem, counter_bytes, partial_bytes, final_bytes;
+  size_t smem, partial_bytes, final_bytes;
 };
 
 int env_int(const char* name, int dflt) {
@@ -416,46 +486,57 @@ int env_int(const char* name, int dflt) {
 // Returns false when the shape is outside the pipelined path.
 bool make_ring_plan(int b, int c, int f, int h, int w, int groups, int per_frame, int dtype, RingPlan* pl) {
   static const int on = env_int("CA_GN_RING", 1);
-  static const int target_kb = env_int("CA_GN_RING_KB", 16);
+  static const int target_kb = env_int("CA_GN_RING_KB", 32);
   static const int want_stages = env_int("CA_GN_RING_STAGES", 6);
   static const int want_folders = env_int("CA_GN_RING_FOLDERS", kMaxFolders);
+  static const int want_ctas = env_int("CA_GN_RING_CTAS", kRingCtasPerSm);
   if (!on) return false;
   if (dtype != CA_BF16 && dtype != CA_F16) return false;
-  if (c % kVecE != 0 || groups <= 0 || c % groups != 0 || groups > kGroupThreads) return false;
-  const int nvec = c / kVecE;
-  if (nvec > kGroupThreads) return false;
+  if (c % kVecE != 0 || groups <= 0 || c % groups != 0) return false;
+  // a worker handles at most kGroupThreads channel vectors of a row; wider rows are cut into slabs of whole groups
+  int slabs = 1;
+  while (slabs <= groups && (groups % slabs != 0 || (c / slabs) % kVecE != 0 || c / slabs / kVecE > kGroupThreads)) ++slabs;
+  if (slabs > groups) return false;
+  const int cs = c / slabs, gs = groups / slabs;
+  if (gs > 2 * kGroupThreads) return false;
+  const int nvec = cs / kVecE;
   const long long rows = per_frame ? (long long)h * w : (long long)f * h * w;
   const long long domains = per_frame ? (long long)b * f : b;
   if (rows <= 0 || rows >= (1ll << 30) || domains <= 0 || domains >= (1ll << 24)) return false;
   const int k = kGroupThreads / nvec;
-  const size_t part_floats = (size_t)k * 2 * c;  // row-lane partial sums
-  const size_t scratch = sizeof(float) * (part_floats + 2 * (size_t)c) + sizeof(float2) * 2 * (size_t)groups;
-  if (scratch >= kRingSmemCap) return false;
-  const long long row_bytes = (long long)c * 2;
+  const size_t part_floats = (size_t)k * 2 * cs;  // row-lane partial sums
+  const size_t scratch = sizeof(float) * (part_floats + 2 * (size_t)cs) + sizeof(float2) * 2 * (size_t)gs;
+  const int ctas = want_ctas < 1 ? 1 : (want_ctas > kRingCtasPerSm ? kRingCtasPerSm : want_ctas);
+  const size_t cap = kRingSmemTotal / ctas - 1536;  // static smem + the 1 KB the driver reserves per CTA
+  if (scratch >= cap) return false;
+  const long long row_bytes = (long long)cs * 2;
   int folders = want_folders < 1 ? 1 : (want_folders > kMaxFolders ? kMaxFolders : want_folders);
   if (folders > domains) folders = (int)domains;
-  const int G = kRingCtasPerSm * sm_count() - folders;  // worker CTAs
+  const int G = ctas * sm_count() - folders;  // worker CTAs
 
   long long j = ((long long)target_kb * 1024) / ((long long)k * row_bytes);
   if (j < 1) j = 1;
   if ((long long)k * j > rows) j = (rows + k - 1) / k;
-  while ((rows + k * j - 1) / (k * j) > G) ++j;  // every worker owns at most one slice per domain
+  while (((rows + k * j - 1) / (k * j)) * slabs > G) ++j;  // every worker owns at most one item per domain
   long long stages;
   for (;; --j) {
-    stages = (long long)(kRingSmemCap - scratch) / ((long long)k * j * row_bytes);
+    stages = (long long)(cap - scratch) / ((long long)k * j * row_bytes);
     if (stages >= 3 || j == 1) break;
   }
   if (stages < 3) return false;
   const long long slice_rows = (long long)k * j;
   const long long spd = (rows + slice_rows - 1) / slice_rows;
-  if (spd > G) return false;
+  if (spd * slabs > G) return false;
   if (stages > want_stages) stages = want_stages;
   if (stages > kMaxStages) stages = kMaxStages;
-  const long long n_items = domains * spd;
+  const long long n_items = domains * spd * slabs;
   if (n_items >= (1ll << 30)) return false;
 
   pl->domains = (int)domains;
   pl->dom_rows = (int)rows;
+  pl->slabs = slabs;
+  pl->cs = cs;
+  pl->gs = gs;
   pl->nvec = nvec;
   pl->k = k;
   pl->slice_rows = (int)slice_rows;
@@ -468,9 +549,8 @@ bool make_ring_plan(int b, int c, int f, int h, int w, int groups, int per_frame
   pl->part_floats = (unsigned int)part_floats;
   pl->smem = (size_t)stages * pl->stage_bytes + scratch;
   if (pl->smem < kFoldBytes) pl->smem = kFoldBytes;  // folder CTAs use the start of the dynamic smem as fold scratch
-  pl->counter_bytes = 0;
-  pl->partial_bytes = sizeof(float2) * (size_t)domains * spd * groups;
-  pl->final_bytes = sizeof(float2) * (size_t)domains * groups;
+  pl->partial_bytes = sizeof(unsigned long long) * (size_t)domains * spd * groups;
+  pl->final_bytes = sizeof(unsigned long long) * (size_t)domains * groups;
   return true;
 }
 
@@ -479,7 +559,7 @@ bool make_ring_plan(int b, int c, int f, int h, int w, int groups, int per_frame
 size_t gn_ring_workspace_bytes(int b, int c, int f, int h, int w, int groups, int per_frame, int dtype) {
   RingPlan pl;
   if (!make_ring_plan(b, c, f, h, w, groups, per_frame, dtype, &pl)) return 0;
-  return pl.counter_bytes + pl.partial_bytes + pl.final_bytes;
+  return pl.partial_bytes + pl.final_bytes;
 }
 
 int gn_ring_launch(const void* x, void* y, const float* gamma, const float* beta, const float* temb, long long temb_ld, int b, int c, int f,
@@ -488,15 +568,16 @@ int gn_ring_launch(const void* x, void* y, const float* gamma, const float* beta
   *handled = false;
   RingPlan pl;
   if (!make_ring_plan(b, c, f, h, w, groups, per_frame, dtype, &pl)) return CA_OK;
-  if (!aligned16(x) || !aligned16(y)) return CA_OK;
-  const size_t need = pl.counter_bytes + pl.partial_bytes + pl.final_bytes;
+  if (!aligned16(x) || !aligned16(y) || !aligned16(gamma) || !aligned16(beta)) return CA_OK;
+  const size_t need = pl.partial_bytes + pl.final_bytes;
   if (!workspace || workspace_bytes < need || !aligned16(workspace)) return CA_OK;
 
   RingParams p{};
   p.x = x; p.y = y; p.gamma = gamma; p.beta = beta; p.temb = temb; p.temb_ld = temb_ld;
   p.c = c; p.groups = groups; p.cpg = c / groups; p.nvec = pl.nvec; p.k = pl.k;
+  p.slabs = pl.slabs; p.cs = pl.cs; p.gs = pl.gs;
   p.gl = 1;
-  while (p.gl < 32 && p.gl * 2 <= p.cpg && p.gl * 2 * groups <= kGroupThreads) p.gl *= 2;
+  while (p.gl < 32 && p.gl * 2 <= p.cpg && p.gl * 2 * pl.gs <= kGroupThreads) p.gl *= 2;
   p.per_frame = per_frame ? 1 : 0; p.f = f; p.eps = eps;
   p.dom_rows = pl.dom_rows; p.domains = pl.domains; p.slice_rows = pl.slice_rows; p.spd = pl.spd;
   p.n_items = pl.n_items; p.stages = pl.stages; p.workers = pl.workers; p.folders = pl.folders;

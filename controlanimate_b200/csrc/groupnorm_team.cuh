@@ -19,4 +19,10 @@ int gn_ring_launch(const void* x, void* y, const float* gamma, const float* beta
                    int h, int w, int groups, float eps, int per_frame, int apply_silu, int dtype, void* workspace,
                    size_t workspace_bytes, cudaStream_t st, bool* handled);
 
+// Two streaming kernels with an L2-resident re-read (groupnorm_stream.cu): same contract; the default native-layout path.
+size_t gn_stream_workspace_bytes(int b, int c, int f, int h, int w, int groups, int per_frame, int dtype);
+int gn_stream_launch(const void* x, void* y, const float* gamma, const float* beta, const float* temb, long long temb_ld, int b, int c,
+                     int f, int h, int w, int groups, float eps, int per_frame, int apply_silu, int dtype, void* workspace,
+                     size_t workspace_bytes, cudaStream_t st, bool* handled);
+
 }  // namespace ca

@@ -144,7 +144,8 @@ struct LnRingParams {
   float eps;
   int rows_per_tile, stages;
   long long n_tiles;
-  unsigned int tile_bytes;
+  unsigned int tile_bytes;  // rows_per_tile rows (+ two fp32 PE rows when pe_staged)
+  int pe_staged;            // the producer copies pe[frame(r0)] and pe[frame(r0) + 1] behind the rows of every tile
 };
 
 __device__ __forceinline__ void ln_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -188,12 +189,19 @@ __global__ void __launch_bounds__((kLnRingWarps + 1) * 32, 2) layernorm_ring_ker
         const long long r0 = t * p.rows_per_tile;
         const long long nr = min((long long)p.rows_per_tile, p.rows - r0);
         const uint32_t total = (uint32_t)(nr * row_bytes);
+        const uint32_t pe_b = p.pe_staged ? (uint32_t)c * 4u : 0u;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], total);
+        mbar_arrive_expect_tx(&full_bar[stage], total + 2 * pe_b);
         const unsigned char* src = reinterpret_cast<const unsigned char*>(p.x) + r0 * row_bytes;
         unsigned char* dst = ring + (size_t)stage * p.tile_bytes;
         constexpr uint32_t kPiece = 8 * 1024;
         for (uint32_t off = 0; off < total; off += kPiece) ln_bulk_load(dst + off, src + off, min(kPiece, total - off), &full_bar[stage]);
+        if (pe_b) {  // a tile spans at most two frames (rows_per_tile <= d): their PE rows ride along (L2-resident table)
+          const int f0 = (int)((r0 / p.d) % p.f), f1 = f0 + 1 == p.f ? 0 : f0 + 1;
+          unsigned char* pd = dst + (size_t)p.rows_per_tile * row_bytes;
+          ln_bulk_load(pd, p.pe + (long long)f0 * c, pe_b, &full_bar[stage]);
+          ln_bulk_load(pd + pe_b, p.pe + (long long)f1 * c, pe_b, &full_bar[stage]);
+        }
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1;
@@ -213,6 +221,8 @@ __global__ void __launch_bounds__((kLnRingWarps + 1) * 32, 2) layernorm_ring_ker
     const int nr = (int)min((long long)p.rows_per_tile, p.rows - r0);
     mbar_wait(&full_bar[stage], phase);
     const unsigned char* tile = ring + (size_t)stage * p.tile_bytes;
+    const float* pe_s = reinterpret_cast<const float*>(tile + (size_t)p.rows_per_tile * row_bytes);
+    const int to_next_frame = p.pe_staged ? (int)min((long long)p.rows_per_tile, (r0 / p.d + 1) * p.d - r0) : 0;
     for (int rb = warp * R; rb < nr; rb += kLnRingWarps * R) {  // warp-uniform trip count (shuffles need the full warp)
       const int r = rb + sub;
       const bool live = r < nr;
@@ -255,7 +265,9 @@ __global__ void __launch_bounds__((kLnRingWarps + 1) * 32, 2) layernorm_ring_ker
       const float2 rstd2 = make_float2(rstd, rstd);
       if (live) {
         const long long row = r0 + r;
-        const float* per = p.pe ? p.pe + (long long)((row / p.d) % p.f) * c : nullptr;
+        const float* per = !p.pe ? nullptr
+                           : p.pe_staged ? pe_s + (r >= to_next_frame ? c : 0)
+                                         : p.pe + (long long)((row / p.d) % p.f) * c;
         T* yr = reinterpret_cast<T*>(p.y) + row * c;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
@@ -268,7 +280,7 @@ __global__ void __launch_bounds__((kLnRingWarps + 1) * 32, 2) layernorm_ring_ker
               const float4 b4 = *reinterpret_cast<const float4*>(s_b + vi * VEC + 4 * j);
               float2 b01 = make_float2(b4.x, b4.y), b23 = make_float2(b4.z, b4.w);
               if (per) {
-                const float4 p4 = __ldg(reinterpret_cast<const float4*>(per + vi * VEC + 4 * j));
+                const float4 p4 = *reinterpret_cast<const float4*>(per + vi * VEC + 4 * j);  // smem (staged) or global
                 b01 = __fadd2_rn(b01, make_float2(p4.x, p4.y));
                 b23 = __fadd2_rn(b23, make_float2(p4.z, p4.w));
               }
@@ -328,7 +340,8 @@ extern "C" __attribute__((visibility("default"))) int ca_layernorm_pe(const void
     p.rows_per_tile = (int)rpt;
     p.stages = ring_stages < 2 ? 2 : (ring_stages > kLnRingStagesMax ? kLnRingStagesMax : ring_stages);
     p.n_tiles = (rows + rpt - 1) / rpt;
-    p.tile_bytes = (unsigned int)(rpt * row_bytes);
+    p.pe_staged = (pe && rpt <= d) ? 1 : 0;
+    p.tile_bytes = (unsigned int)(rpt * row_bytes + (p.pe_staged ? 2 * (size_t)c * sizeof(float) : 0));
     const size_t smem_ring = (size_t)p.stages * p.tile_bytes + 2 * (size_t)c * sizeof(float);
     if (smem_ring <= 100 * 1024) {
       const int threads = (kLnRingWarps + 1) * 32;

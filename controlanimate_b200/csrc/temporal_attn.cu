@@ -19,8 +19,8 @@
 //  * mbarrier full/empty ring (3 stages), one producer warp, S consumer warps (one site each).
 //  * per warp: S = Q K^T with mma.sync m16n8k16 (+ one m16n8k8 step when head_dim % 16 == 8),
 //    fp32 scores, warp-shuffle row max / row sum (4 lanes per row), P split into bf16 hi + lo so
-//    that P V carries ~16 mantissa bits, O scaled by 1/rowsum in fp32, staged in smem and written
-//    with a TMA tensor store (fully coalesced, clipped at tensor bounds).
+//    that P V carries ~16 mantissa bits, O scaled by 1/rowsum in fp32, staged in the consumed Q tile and
+//    written with 16-byte streaming stores (whole head rows; no TMA store on the consumers' critical path).
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -36,6 +36,9 @@ struct AttnParams {
   long long units;   // b * site_tiles * heads
   float scale_log2;  // scale * log2(e)
   uint32_t tile_bytes;  // bytes of one operand tile in smem (S*f*hdp*2, padded to 128)
+  // output addressing for the vectorised write-out: row(b, frame, site) = b*batch_rows + frame*frame_rows + site*site_rows
+  void* o;
+  long long ldo, batch_rows, frame_rows, site_rows;
 };
 
 template <typename T>
@@ -99,7 +102,7 @@ __device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, uint32
 template <typename T, int MT, int HD, bool FULLF>
 __global__ void __launch_bounds__(288, MT == 1 ? 2 : 1)
     temporal_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                         const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
+                         const __grid_constant__ CUtensorMap map_v,
                          const AttnParams p) {
   using M = MmaT<T>;
   constexpr int NT = 2 * MT;
@@ -317,22 +320,29 @@ __global__ void __launch_bounds__(288, MT == 1 ? 2 : 1)
           }
         }
     }
-    // ---- TMA store of this site's [f][hd] block, then release the stage ----
-    fence_proxy_async();
+    // ---- write this site's [f][hd] block with 16-byte stores straight from the staging tile, then release the stage.
+    // (r01d: a TMA tensor store here cost 23 % of the consumers' time in cp.async.bulk.wait_group.read -- the store
+    // queues behind the producer's loads in the TMA unit and the stage cannot be handed back before it has been read.)
     __syncwarp();
-    if (lane == 0) {
-      tma_store_5d(&map_o, base, 0, 0, st * S + warp, head, bi);
-      bulk_commit();
-      bulk_wait_read<0>();
-      mbar_arrive(&empty_bar[stage]);
+    {
+      const int site = st * S + warp;
+      if (site < p.d) {
+        const int nvr = hd >> 3;  // 16-byte vectors per row
+        T* og = reinterpret_cast<T*>(p.o) + ((long long)bi * p.batch_rows + (long long)site * p.site_rows) * p.ldo + head * hd;
+        for (int v = lane; v < f * nvr; v += 32) {
+          const int row = v / nvr, ch = v - row * nvr;
+          const uint4 val = *reinterpret_cast<const uint4*>(base + row * pitch + ch * 16);
+          stg_stream(og + (long long)row * p.frame_rows * p.ldo + ch * 8, val);
+        }
+      }
     }
     __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
     if (++stage == kStages) {
       stage = 0;
       phase ^= 1;
     }
   }
-  if (lane == 0) bulk_wait<0>();
 }
 
 // 5-D map (head_dim, frame, site, head, batch) over a token matrix with row stride `ld` elements where
@@ -382,6 +392,7 @@ extern "C" __attribute__((visibility("default"))) int ca_temporal_attn_core(cons
   p.units = (long long)b * p.site_tiles * heads;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.tile_bytes = (uint32_t)(S * site_bytes);
+  p.o = o; p.ldo = ldo;
   const size_t smem = (size_t)kStages * 3 * p.tile_bytes + 32 * p.hdp * 2 + 128;
   CA_CHECK_ARG(smem <= 220 * 1024, "temporal_attn_core: tile does not fit shared memory");
 
@@ -389,11 +400,11 @@ extern "C" __attribute__((visibility("default"))) int ca_temporal_attn_core(cons
   const long long batch_rows = (long long)f * d;
   const long long frame_rows = seq_major ? 1 : d;
   const long long site_rows = seq_major ? f : 1;
-  CUtensorMap mq, mk, mv, mo;
+  p.batch_rows = batch_rows; p.frame_rows = frame_rows; p.site_rows = site_rows;
+  CUtensorMap mq, mk, mv;
   if (!make_attn_map(&mq, q, dtype, b, f, d, heads, head_dim, ldq, batch_rows, frame_rows, site_rows, p.hdp, p.fpad, S) ||
       !make_attn_map(&mk, k, dtype, b, f, d, heads, head_dim, ldk, batch_rows, frame_rows, site_rows, p.hdp, p.fpad, S) ||
-      !make_attn_map(&mv, v, dtype, b, f, d, heads, head_dim, ldv, batch_rows, frame_rows, site_rows, p.hdp, p.fpad, S) ||
-      !make_attn_map(&mo, o, dtype, b, f, d, heads, head_dim, ldo, batch_rows, frame_rows, site_rows, p.hdp, f, 1))
+      !make_attn_map(&mv, v, dtype, b, f, d, heads, head_dim, ldv, batch_rows, frame_rows, site_rows, p.hdp, p.fpad, S))
     return CA_ERR_CUDA;
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -405,7 +416,7 @@ extern "C" __attribute__((visibility("default"))) int ca_temporal_attn_core(cons
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)sm_count() * per_sm;
     if (grid > p.units) grid = p.units;
-    kernel<<<(unsigned)grid, threads, smem, st>>>(mq, mk, mv, mo, p);
+    kernel<<<(unsigned)grid, threads, smem, st>>>(mq, mk, mv, p);
     CA_CUDA(cudaGetLastError());
     return CA_OK;
   };

@@ -151,6 +151,35 @@ def temporal_attention_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *
     return o
 
 
+def cross_attention_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, frames: int, sites: int, heads: int,
+                         ctx_of_frame: Optional[torch.Tensor] = None, scale: Optional[float] = None,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(q k^T scale) v of every latent site against the prompt tokens (row N2, cross-attention of the spatial transformer).
+
+    q [(frames*sites), C] token-major; k, v [n_ctx, L, C] (may be column slices of one fused [n_ctx, L, 2C] projection);
+    ctx_of_frame int32 [frames] or None (frame n -> prompt n // (frames // n_ctx)).  Raises ValueError for head sizes / prompt
+    lengths outside the built variants (the caller decides what to do then)."""
+    _cuda(q, k, v)
+    T, Cq = q.shape
+    if T != frames * sites or k.dim() != 3 or k.shape != v.shape or k.shape[2] != Cq or Cq % heads:
+        raise ValueError("q must be [(frames*sites), C] and k/v [n_ctx, L, C]")
+    if q.stride(1) != 1 or k.stride(2) != 1 or v.stride(2) != 1:
+        raise ValueError("q/k/v rows must be dense")
+    if ctx_of_frame is not None and (ctx_of_frame.dtype != torch.int32 or ctx_of_frame.numel() != frames or not ctx_of_frame.is_cuda):
+        raise ValueError("ctx_of_frame must be a CUDA int32 tensor with one entry per frame")
+    hd = Cq // heads
+    o = torch.empty((T, Cq), dtype=q.dtype, device=q.device) if out is None else out
+    if o.stride(1) != 1 or o.shape != q.shape:
+        raise ValueError("bad out tensor")
+    scale = hd ** -0.5 if scale is None else scale
+    n_ctx, L_kv = k.shape[0], k.shape[1]
+    with P.span("cross_attn_core", 1, 2.0 * T * Cq * q.element_size(), 4.0 * L_kv * Cq * T):
+        L.check(L.load().ca_cross_attn_core(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), frames, sites, heads, hd, n_ctx,
+                                            L_kv, q.stride(0), k.stride(1), v.stride(1), o.stride(0), k.stride(0), v.stride(0),
+                                            _ptr(ctx_of_frame), float(scale), _dt(q), _stream()), "ca_cross_attn_core")
+    return o
+
+
 def residual_merge(per_net: Sequence[Sequence[torch.Tensor]], scales: Sequence[Sequence[float]], dst: Sequence[torch.Tensor], *,
                    frames: int, add_into_dst: bool, layout: int) -> None:
     """dst_i (=|+=) Σ_k scales[k][i] * per_net[k][i] in one launch (kernel 3).

@@ -104,6 +104,21 @@ int ca_temporal_attn_core(const void* q, const void* k, const void* v, void* o, 
                           int head_dim, long long ldq, long long ldk, long long ldv, long long ldo, int seq_major,
                           float scale, int dtype, void* stream);
 
+/* Cross-attention core of the spatial transformer: every latent site attends to the
+ * kv_len <= 96 prompt tokens, O = softmax(Q K^T * scale) V per (frame, head).
+ * Replaces the attention arithmetic of BasicTransformerBlock.attn2 (reference animatediff/models/attention.py:283-289
+ * -> modules/attention_processor.py:56-62 baddbmm/softmax/bmm, :247-256 SDPA).
+ *   q, o   [n_frames * d, heads*head_dim] token-major rows (row strides ldq / ldo elements), token = frame*d + site
+ *   k, v   [n_ctx, kv_len, heads*head_dim] rows (row strides ldk / ldv, prompt strides ctx_stride_k / ctx_stride_v);
+ *          they may be column slices of one fused [n_ctx, kv_len, 2C] projection
+ *   ctx_of_frame  device int32 [n_frames] prompt index of every frame, or NULL: frame n uses prompt n / (n_frames/n_ctx)
+ *   constraints: head_dim in {40, 80, 160} (the SD1.5 widths), kv_len <= 96, dtype bf16/f16, strides multiples of 8
+ *   returns CA_ERR_UNSUPPORTED for other head_dim / kv_len (the caller keeps its library path for those) */
+int ca_cross_attn_core(const void* q, const void* k, const void* v, void* o, int n_frames, int d, int heads, int head_dim,
+                       int n_ctx, int kv_len, long long ldq, long long ldk, long long ldv, long long ldo,
+                       long long ctx_stride_k, long long ctx_stride_v, const int* ctx_of_frame, float scale, int dtype,
+                       void* stream);
+
 /* Dense projection on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA operands):
  *   y = epilogue(x @ w^T + bias) (+ residual)
  * Replaces the nn.Linear projections of the motion module: to_q/to_k/to_v (fused as one [3C, C]

@@ -50,7 +50,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--out", default="gpurun_out/microbench.json")
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--only", default="", help="comma list of kernel families: gn,ln,attn,gemm,merge")
+    ap.add_argument("--only", default="", help="comma list of kernel families: gn,ln,attn,xattn,gemm,merge")
     args = ap.parse_args()
     only = set(filter(None, args.only.split(",")))
     want = lambda fam: not only or fam in only  # noqa: E731
@@ -106,6 +106,18 @@ def main():
                 us, mn = timeit(lambda: ops.temporal_attention_core(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], batch=b, frames=f,
                                                                     sites=s * s, heads=8, out=o), args.iters, flush)
                 add("temporal_attn_core", f"b{b} f{f} d{s * s} c{c} (hd {c // 8})", us, mn, 4.0 * T * c * 2, 4.0 * f * c * T)
+            if f == 16 and want("xattn") and c // 8 in (40, 80, 160):
+                # cross-attention of the spatial transformer: every site against 77 prompt tokens, 2 prompts (CFG halves)
+                qx = torch.randn(T, c, device=dev, dtype=bt)
+                kvx = torch.randn(b, 77, 2 * c, device=dev, dtype=bt)
+                us, mn = timeit(lambda: ops.cross_attention_core(qx, kvx[:, :, :c], kvx[:, :, c:], frames=b * f, sites=s * s, heads=8,
+                                                                 out=o), args.iters, flush)
+                add("cross_attn_core", f"frames{b * f} d{s * s} c{c} (hd {c // 8}) L77", us, mn, 2.0 * T * c * 2, 4.0 * 77 * c * T)
+                qh = qx.reshape(b * f, s * s, 8, c // 8).transpose(1, 2)
+                kh = kvx[:, :, :c].reshape(b, 77, 8, c // 8).transpose(1, 2).repeat_interleave(f, dim=0)
+                vh = kvx[:, :, c:].reshape(b, 77, 8, c // 8).transpose(1, 2).repeat_interleave(f, dim=0)
+                us, mn = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qh, kh, vh), args.iters, flush)
+                add("torch_sdpa(yardstick)", f"frames{b * f} d{s * s} c{c} (hd {c // 8}) L77", us, mn, 2.0 * T * c * 2, 4.0 * 77 * c * T)
             if f == 16 and want("gemm"):
                 # the motion module's GEMMs: fused QKV, out-proj + residual, GEGLU, FF out
                 w3 = torch.randn(3 * c, c, device=dev, dtype=bt) * c ** -0.5

@@ -85,6 +85,24 @@ def test_groupnorm_silu(ops, case, layout, dtype):
         assert relerr(y, ref) <= REL[dtype], (case, layout, dtype, silu)
 
 
+@pytest.mark.parametrize("env", [{"CA_GN_STREAM": "1"}, {"CA_GN_RING": "0"}, {"CA_GN_RING": "0", "CA_GN_TEAM": "0"}],
+                         ids=["stream-pair", "team", "split"])
+def test_groupnorm_alternative_paths(env):
+    """The native-layout GroupNorm has three measured alternatives behind ca_groupnorm_silu (streaming pair, team kernel,
+    split launches); the path is chosen once per process from the environment, so each is re-checked in a child process
+    against the same oracle cases."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("CA_GN_CHILD") == "1":
+        pytest.skip("already inside a child run")
+    child_env = dict(os.environ, CA_GN_CHILD="1", **env)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", __file__, "-k",
+                        "test_groupnorm_silu and bfhwc or test_groupnorm_row_strided"], env=child_env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_groupnorm_row_strided_temb_and_determinism(ops):
     """temb rows may be column slices of one wide [b, sum C] buffer (layers.TembBank); results are bit-reproducible."""
     b, c, f, h, w = 2, 320, 4, 32, 32
@@ -187,6 +205,43 @@ def test_temporal_attention_core(ops, case, dtype):
     o2 = ops.temporal_attention_core(g[:, :C].contiguous(), g[:, C:2 * C].contiguous(), g[:, 2 * C:].contiguous(),
                                      batch=b, frames=f, sites=d, heads=heads)
     assert torch.equal(o, o2)
+
+
+X_CASES = [
+    # frames, sites, heads, head_dim, n_ctx, kv_len, explicit frame->prompt map
+    (4, 200, 8, 40, 2, 77, False),    # ragged last query tile (200 = 128 + 72), two prompts x two frames
+    (6, 64, 8, 80, 3, 77, True),      # interleaved frame -> prompt map (ControlNet: frame % n_prompts)
+    (2, 256, 8, 160, 2, 81, False),   # IP-Adapter length (77 + 4 image tokens): 96-key variant, two P V passes
+    (3, 130, 4, 40, 1, 5, False),     # very short prompt, one prompt for every frame
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("case", X_CASES)
+def test_cross_attention_core(ops, case, dtype):
+    """Row N2: cross-attention of the spatial transformer against the oracle's attention_core (attention_processor.py:56-62)."""
+    frames, d, heads, hd, n_ctx, L, use_map = case
+    C = heads * hd
+    q = synth.tensor(13, f"xattn.q{case}", (frames * d, C)).to(dtype)
+    kv = synth.tensor(13, f"xattn.kv{case}", (n_ctx, L, 2 * C)).to(dtype)
+    cmap = (torch.arange(frames) % n_ctx) if use_map else (torch.arange(frames) // (frames // n_ctx))
+    kf, vf = kv[:, :, :C].float()[cmap], kv[:, :, C:].float()[cmap]
+    ref = R.attention_core(q.float().reshape(frames, d, C), kf, vf, heads).reshape(frames * d, C)
+    g = kv.cuda()
+    o = ops.cross_attention_core(q.cuda(), g[:, :, :C], g[:, :, C:], frames=frames, sites=d, heads=heads,
+                                 ctx_of_frame=cmap.to(torch.int32).cuda() if use_map else None)
+    assert relerr(o, ref) <= REL[dtype], case
+
+
+def test_cross_attention_rejects_unbuilt_variants(ops):
+    q = torch.zeros(64, 8 * 64, device="cuda", dtype=torch.bfloat16)
+    kv = torch.zeros(1, 77, 8 * 64, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        ops.cross_attention_core(q, kv, kv, frames=1, sites=64, heads=8)        # head_dim 64 is not an SD1.5 width
+    q = torch.zeros(64, 320, device="cuda", dtype=torch.bfloat16)
+    kv = torch.zeros(1, 200, 320, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        ops.cross_attention_core(q, kv, kv, frames=1, sites=64, heads=8)        # prompt longer than 96 tokens
 
 
 def test_temporal_attention_rejects_long_sequences(ops):
