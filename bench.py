@@ -35,6 +35,21 @@ COND_SCALE = [1.0, 0.5]
 OVERLAP = 4
 
 
+def ncu_traffic(family: str):
+    """DRAM bytes per launch of `family` from the newest committed ncu launch list (profiles/r*_traffic.json, written by
+    scripts/launch_traffic.py from the same bench command under ncu); None when no capture is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if not files:
+        return None
+    try:
+        with open(files[-1]) as fh:
+            d = json.load(fh)
+        return float(d["families"][family]["traffic_per_launch"])
+    except (KeyError, ValueError, OSError):
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -299,6 +314,8 @@ def run_b200(args):
         value = world * f / (DDIM_STEPS * ms * 1e-3)
         e2e = world * f / (DDIM_STEPS * ms_e2e * 1e-3)
         top = kern["dominant"]
+        top["traffic"] = ncu_traffic(top["kernel"])
+        top["traffic_source"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu launch list of the same step (profiles/)"
         line = {
             "metric": "denoised frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

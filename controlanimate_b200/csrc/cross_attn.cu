@@ -144,12 +144,13 @@ __global__ void __launch_bounds__(kXWarps * 32) cross_attn_kernel(const __grid_c
 
   const int r0 = lane >> 2, cq = (lane & 3) * 2;
   int cur_ctx = -1, cur_head = -1;
+  // (qt, fr, head, blk) of the current unit are advanced incrementally; only thread 0 decodes (the look-ahead unit)
+  int qt = u0 % p.q_tiles, fr = (u0 / p.q_tiles) % fpb, head = ((u0 / p.q_tiles) / fpb) % p.heads, blk = ((u0 / p.q_tiles) / fpb) / p.heads;
+  int st = 0;
+  uint32_t phase = 0;
   for (int u = u0; u < u1; ++u) {
-    int frame, head, qt;
-    decode(u, frame, head, qt);
+    const int frame = blk * fpb + fr;
     const int ctx = p.ctx_of_frame ? __ldg(p.ctx_of_frame + frame) : frame / p.frames_per_ctx;
-    const int st = (u - u0) % kXStages;
-    const uint32_t phase = (uint32_t)((u - u0) / kXStages) & 1u;
 
     if (ctx != cur_ctx || head != cur_head) {  // CTA-uniform
       __syncthreads();                          // everyone is done with the previous K/V
@@ -199,35 +200,42 @@ __global__ void __launch_bounds__(kXWarps * 32) cross_attn_kernel(const __grid_c
       }
     }
 
-    // ---- softmax over the keys (fp32, exp2 with folded scale) -> P as 16-bit A fragments ----
+    // ---- softmax over the keys (fp32) -> P as 16-bit A fragments.  The row maximum is taken on the raw scores (scale > 0),
+    // scale*log2(e) and the maximum are folded into one packed FFMA2 per score pair, only the n-tiles that contain padded
+    // keys are masked: r01d's capture showed this kernel issue-bound on the per-score softmax arithmetic. ----
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
+    for (int nt = 0; nt < NT; ++nt) {
+      if (nt * 8 + 8 > p.L) {  // warp-uniform: at most the last two tiles
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int key = nt * 8 + cq + (j & 1);
-        const float s = key < p.L ? sacc[nt][j] * p.scale_log2 : -INFINITY;
-        sacc[nt][j] = s;
-        mx[j >> 1] = fmaxf(mx[j >> 1], s);
+        for (int j = 0; j < 4; ++j)
+          if (nt * 8 + cq + (j & 1) >= p.L) sacc[nt][j] = -INFINITY;
       }
+      mx[0] = fmaxf(mx[0], fmaxf(sacc[nt][0], sacc[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(sacc[nt][2], sacc[nt][3]));
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
       mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
     }
-    float sum[2] = {0.f, 0.f};
+    const float2 sl2 = make_float2(p.scale_log2, p.scale_log2);
+    const float2 nm0 = make_float2(-mx[0] * p.scale_log2, -mx[0] * p.scale_log2);
+    const float2 nm1 = make_float2(-mx[1] * p.scale_log2, -mx[1] * p.scale_log2);
+    float2 sum0 = make_float2(0.f, 0.f), sum1 = make_float2(0.f, 0.f);
     uint32_t pf[NT][2];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      float e[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        e[j] = exp2f(sacc[nt][j] - mx[j >> 1]);  // exp2f(-inf) = 0 for masked keys
-        sum[j >> 1] += e[j];
-      }
-      pf[nt][0] = pack2(e[0], e[1], T());
-      pf[nt][1] = pack2(e[2], e[3], T());
+      const float2 t0 = __ffma2_rn(make_float2(sacc[nt][0], sacc[nt][1]), sl2, nm0);
+      const float2 t1 = __ffma2_rn(make_float2(sacc[nt][2], sacc[nt][3]), sl2, nm1);
+      const float2 e0 = make_float2(exp2f(t0.x), exp2f(t0.y));  // exp2f(-inf) = 0 for masked keys
+      const float2 e1 = make_float2(exp2f(t1.x), exp2f(t1.y));
+      sum0 = __fadd2_rn(sum0, e0);
+      sum1 = __fadd2_rn(sum1, e1);
+      pf[nt][0] = pack2(e0.x, e0.y, T());
+      pf[nt][1] = pack2(e1.x, e1.y, T());
     }
+    float sum[2] = {sum0.x + sum0.y, sum1.x + sum1.y};
     float inv_sum[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -281,6 +289,20 @@ __global__ void __launch_bounds__(kXWarps * 32) cross_attn_kernel(const __grid_c
     if (threadIdx.x == 0 && u + kXStages - 1 < u1) {
       fence_proxy_async();
       issue(u + kXStages - 1);
+    }
+    if (++qt == p.q_tiles) {
+      qt = 0;
+      if (++fr == fpb) {
+        fr = 0;
+        if (++head == p.heads) {
+          head = 0;
+          ++blk;
+        }
+      }
+    }
+    if (++st == kXStages) {
+      st = 0;
+      phase ^= 1u;
     }
   }
 }

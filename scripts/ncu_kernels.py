@@ -32,6 +32,10 @@ for _ in range(3):
         if which in ("all", "attn"):
             qkv = torch.randn(T, 3 * c, device=dev, dtype=bt)
             ops.temporal_attention_core(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], batch=b, frames=f, sites=s * s, heads=8)
+        if which in ("all", "xattn"):
+            qx = torch.randn(T, c, device=dev, dtype=bt)
+            kvx = torch.randn(b, 77, 2 * c, device=dev, dtype=bt)
+            ops.cross_attention_core(qx, kvx[:, :, :c], kvx[:, :, c:], frames=b * f, sites=s * s, heads=8)
         if which in ("all", "gemm"):
             w3 = torch.randn(3 * c, c, device=dev, dtype=bt)
             w1 = torch.randn(c, c, device=dev, dtype=bt)
