@@ -666,8 +666,12 @@ extern "C" __attribute__((visibility("default"))) int ca_groupnorm_silu(const vo
   int rc = make_plan(b, c, f, h, w, groups, per_frame, layout, dtype, &pl);
   if (rc != CA_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (layout == CA_LAYOUT_BFHWC) {  // native layout: [opt-in streaming pair,] pipelined slice ring, else persistent team kernel
+  if (layout == CA_LAYOUT_BFHWC) {  // native layout: small domains -> one CTA per (domain, group slab); else [opt-in streaming pair,] pipelined slice ring,
+    // else persistent team kernel
     bool handled = false;
+    rc = gn_slab_launch(x, y, gamma, beta, temb, temb_ld > 0 ? temb_ld : c, b, c, f, h, w, groups, eps, per_frame, apply_silu, dtype, st,
+                        &handled);
+    if (rc != CA_OK || handled) return rc;
     rc = gn_stream_launch(x, y, gamma, beta, temb, temb_ld > 0 ? temb_ld : c, b, c, f, h, w, groups, eps, per_frame, apply_silu, dtype,
                           workspace, workspace_bytes, st, &handled);
     if (rc != CA_OK || handled) return rc;

@@ -25,4 +25,9 @@ int gn_stream_launch(const void* x, void* y, const float* gamma, const float* be
                      int f, int h, int w, int groups, float eps, int per_frame, int apply_silu, int dtype, void* workspace,
                      size_t workspace_bytes, cudaStream_t st, bool* handled);
 
+// Small-domain kernel (groupnorm_slab.cu): a CTA owns every row of (domain, slab of whole groups); no workspace, no exchange.
+int gn_slab_launch(const void* x, void* y, const float* gamma, const float* beta, const float* temb, long long temb_ld, int b, int c,
+                   int f, int h, int w, int groups, float eps, int per_frame, int apply_silu, int dtype, cudaStream_t st,
+                   bool* handled);
+
 }  // namespace ca

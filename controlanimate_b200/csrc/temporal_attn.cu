@@ -96,11 +96,11 @@ __device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, uint32
 }
 
 // MT = ceil(f / 16) query m-tiles (1 or 2); keys are handled as 2*MT n-tiles of 8.  HD > 0 fixes head_dim (and the smem row
-// pitch) at compile time and FULLF says f == 16*MT exactly, so the loops unroll without per-tile bounds tests; r01d's
+// pitch) at compile time and F > 0 the frame count, so the loops unroll without per-tile bounds tests; r01d's
 // capture showed the generic kernel issue-bound on index arithmetic (662 warp instructions per (site, head) unit, only 22
 // of them HMMA, 64-bit div/mod per unit), not on HBM.
-template <typename T, int MT, int HD, bool FULLF>
-__global__ void __launch_bounds__(288, MT == 1 ? 2 : 1)
+template <typename T, int MT, int HD, int F>
+__global__ void __launch_bounds__(288, (MT == 1 || F > 0) ? 2 : 1)
     temporal_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                          const __grid_constant__ CUtensorMap map_v,
                          const AttnParams p) {
@@ -174,8 +174,8 @@ __global__ void __launch_bounds__(288, MT == 1 ? 2 : 1)
   if (warp > S) return;
 
   // ===== consumers: warp w owns site (tile_site0 + w) =====
-  const int f = FULLF ? 16 * MT : p.f, hd = HD > 0 ? HD : p.hd;
-  const int site_bytes = (FULLF ? 16 * MT : p.fpad) * pitch;
+  const int f = F > 0 ? F : p.f, hd = HD > 0 ? HD : p.hd;
+  const int site_bytes = (F > 0 ? (F + 7) / 8 * 8 : p.fpad) * pitch;
   const int r0 = lane >> 2, cq = (lane & 3) * 2;  // fragment row / column-pair
   int stage = 0;
   uint32_t phase = 0;
@@ -272,21 +272,23 @@ __global__ void __launch_bounds__(288, MT == 1 ? 2 : 1)
       }
     }
 
-    // ---- O = P V, 64 output columns at a time; staged into this warp's (consumed) Q tile ----
+    // ---- O = P V, OCH output columns at a time (32 with two query m-tiles: keeps the accumulators at 32 registers so two
+    // CTAs fit one SM); staged into this warp's (consumed) Q tile ----
+    constexpr int OCH = MT == 2 ? 32 : 64;
 #pragma unroll
-    for (int c0 = 0; c0 < hd; c0 += 64) {
-      float oacc[MT][8][4];
+    for (int c0 = 0; c0 < hd; c0 += OCH) {
+      float oacc[MT][OCH / 8][4];
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
+        for (int nt = 0; nt < OCH / 8; ++nt)
 #pragma unroll
           for (int j = 0; j < 4; ++j) oacc[mt][nt][j] = 0.f;
 #pragma unroll
       for (int kt = 0; kt < MT; ++kt) {  // 16 keys per step
         if (kt * 16 < f) {
 #pragma unroll
-          for (int nt = 0; nt < 8; ++nt) {
+          for (int nt = 0; nt < OCH / 8; ++nt) {
             if (c0 + nt * 8 < hd) {
               uint32_t b0, b1;
               ldsm_x2_trans(b0, b1, v_s + (kt * 16 + (lane & 15)) * pitch + (c0 + nt * 8) * 2);
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(288, MT == 1 ? 2 : 1)
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < OCH / 8; ++nt) {
           const int col = c0 + nt * 8 + cq;
           if (col < hd) {
 #pragma unroll
@@ -422,12 +424,15 @@ extern "C" __attribute__((visibility("default"))) int ca_temporal_attn_core(cons
   };
   const bool two = f > 16;
   if (dtype == CA_BF16) {
-    if (f == 16) {  // the AnimateDiff window length: head_dim 40 / 80 / 160 are the SD1.5 motion-module widths
-      if (head_dim == 40) return run(temporal_attn_kernel<__nv_bfloat16, 1, 40, true>);
-      if (head_dim == 80) return run(temporal_attn_kernel<__nv_bfloat16, 1, 80, true>);
-      if (head_dim == 160) return run(temporal_attn_kernel<__nv_bfloat16, 1, 160, true>);
-    }
-    return two ? run(temporal_attn_kernel<__nv_bfloat16, 2, 0, false>) : run(temporal_attn_kernel<__nv_bfloat16, 1, 0, false>);
+    // the AnimateDiff window lengths (8 / 16 / 24 / 32 frames) x the SD1.5 motion-module head widths are compile-time
+    // specialisations; everything else takes the generic kernel
+#define CA_TA_CASE(F_, HD_) if (f == F_ && head_dim == HD_) return run(temporal_attn_kernel<__nv_bfloat16, (F_ > 16 ? 2 : 1), HD_, F_>)
+    CA_TA_CASE(16, 40); CA_TA_CASE(16, 80); CA_TA_CASE(16, 160);
+    CA_TA_CASE(8, 40); CA_TA_CASE(8, 80); CA_TA_CASE(8, 160);
+    CA_TA_CASE(24, 40); CA_TA_CASE(24, 80); CA_TA_CASE(24, 160);
+    CA_TA_CASE(32, 40); CA_TA_CASE(32, 80); CA_TA_CASE(32, 160);
+#undef CA_TA_CASE
+    return two ? run(temporal_attn_kernel<__nv_bfloat16, 2, 0, 0>) : run(temporal_attn_kernel<__nv_bfloat16, 1, 0, 0>);
   }
-  return two ? run(temporal_attn_kernel<__half, 2, 0, false>) : run(temporal_attn_kernel<__half, 1, 0, false>);
+  return two ? run(temporal_attn_kernel<__half, 2, 0, 0>) : run(temporal_attn_kernel<__half, 1, 0, 0>);
 }
