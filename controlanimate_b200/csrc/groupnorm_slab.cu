@@ -1,8 +1,9 @@
-// Kernel (2), native-layout small-domain path: GroupNorm + SiLU (+ time-embedding add) on a BFHWC video activation when
-// ALL rows of a statistics domain for a slab of whole groups fit one CTA's shared memory (the 16x16 and 8x8 latent levels
-// of SD1.5: 64-256 rows).  Groups are independent, so a CTA that owns every row of (domain, S groups) needs no cross-CTA
-// exchange at all: cp.async the [rows][S*cpg] slab into smem, statistics, normalise, store -- one plain launch, one HBM
-// read + one HBM write.
+// Kernel (2), native-layout slab path: GroupNorm + SiLU (+ time-embedding add) on a BFHWC video activation when the rows of
+// a statistics domain for a slab of whole groups fit the shared memory of ONE CTA (16x16 / 8x8 latent levels) or of one
+// thread-block CLUSTER of up to 8 CTAs (32x32 ... 96x96).  Groups are independent, so the CTAs that own every row of
+// (domain, S groups) exchange nothing with the rest of the grid: cp.async the [rows][S*cpg] slab into smem, statistics,
+// [per-group (mean, M2) partials pushed into every peer's smem over DSMEM + one barrier.cluster], normalise, store -- one
+// plain launch, no workspace, no spin-waits, one HBM read + one HBM write.
 //
 // Replaces InflatedGroupNorm.forward + F.silu (reference animatediff/models/resnet.py:23-31, 191-192, 199-208) and the
 // per-frame transformer-entry GroupNorms (motion_module.py:144, attention.py:131) at those levels.
@@ -14,13 +15,16 @@
 
 #include "common.cuh"
 #include "groupnorm_team.cuh"
+#include "tma.cuh"
 
 namespace ca {
 namespace {
 
 constexpr int kSlabThreads = 256;
 constexpr int kVecE = 8;
-constexpr size_t kSlabTileCap = 56 * 1024;
+constexpr size_t kSlabTileTarget = 40 * 1024;  // per-CTA slab the plan aims for (4-5 CTAs per SM overlap load / compute / store)
+constexpr size_t kSlabTileCap = 96 * 1024;     // hard limit (2 CTAs per SM)
+constexpr int kMaxCluster = 8;
 
 struct SlabParams {
   const void* x;
@@ -35,6 +39,7 @@ struct SlabParams {
   int per_frame, f;
   float eps;
   int dom_rows;
+  int R, rows_per;  // cluster size (CTAs sharing one (domain, slab)) and rows per CTA
 };
 
 __device__ __forceinline__ float tanh_fast_b(float v) {
@@ -49,24 +54,33 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 template <typename T, bool kSilu>
 __global__ void __launch_bounds__(kSlabThreads) gn_slab_kernel(const SlabParams p) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  const int Cs = p.seg_c, nvs = p.nvs, k = p.k, rows = p.dom_rows;
-  uint4* tile = reinterpret_cast<uint4*>(s_raw);                                    // [rows][nvs]
-  float* s_part = reinterpret_cast<float*>(s_raw + (size_t)rows * Cs * sizeof(T));  // [k][2][Cs]
-  float* s_ch = s_part + (size_t)k * 2 * Cs;                                        // [2][Cs]
-  float2* s_fin = reinterpret_cast<float2*>(s_ch + 2 * Cs);                         // [S] (mean, rstd)
+  const int Cs = p.seg_c, nvs = p.nvs, k = p.k, R = p.R;
+  uint4* tile = reinterpret_cast<uint4*>(s_raw);                                          // [rows_per][nvs]
+  float* s_part = reinterpret_cast<float*>(s_raw + (size_t)p.rows_per * Cs * sizeof(T));  // [k][2][Cs]
+  float* s_ch = s_part + (size_t)k * 2 * Cs;                                              // [2][Cs]
+  float2* s_fin = reinterpret_cast<float2*>(s_ch + 2 * Cs);                               // [S] (mean, rstd)
+  float2* s_x = s_fin + p.S;                                                              // [R][S] partials of the cluster
 
   const int tid = threadIdx.x;
-  const int dom = blockIdx.x / p.slabs_per_dom, slab = blockIdx.x - dom * p.slabs_per_dom;
+  const int rank = R > 1 ? (int)cluster_ctarank() : 0;
+  const int unit = blockIdx.x / R;  // (domain, slab)
+  const int dom = unit / p.slabs_per_dom, slab = unit - dom * p.slabs_per_dom;
   const int bi = p.per_frame ? dom / p.f : dom;
   const bool on = tid < nvs * k;
   const int cv = tid % nvs, rl = tid / nvs;
   const long long co = (long long)slab * Cs;
-  const T* xs = reinterpret_cast<const T*>(p.x) + (long long)dom * rows * p.c + co + cv * kVecE;
-  T* ys = reinterpret_cast<T*>(p.y) + (long long)dom * rows * p.c + co + cv * kVecE;
+  const int r_begin = rank * p.rows_per;
+  const int rows = min(p.rows_per, p.dom_rows - r_begin);  // >= 1 by construction of the plan
+  const T* xs = reinterpret_cast<const T*>(p.x) + ((long long)dom * p.dom_rows + r_begin) * p.c + co + cv * kVecE;
+  T* ys = reinterpret_cast<T*>(p.y) + ((long long)dom * p.dom_rows + r_begin) * p.c + co + cv * kVecE;
 
   if (on)
     for (int r = rl; r < rows; r += k) cp_async16(&tile[r * nvs + cv], xs + (long long)r * p.c);
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  // "every CTA of the cluster has started" must hold before anyone writes into a peer's shared memory: arrive now, wait only
+  // right before the DSMEM pushes, so the barrier latency hides behind the load and the statistics
+  if (R > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   // ---- statistics: per-channel sums shifted by row 0 (packed f32x2), row lanes added in fixed order, channels -> groups ----
@@ -124,6 +138,7 @@ __global__ void __launch_bounds__(kSlabThreads) gn_slab_kernel(const SlabParams 
     }
   }
   __syncthreads();
+  if (R > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   {
     const int L = p.gl;
     const float inv_cpg = 1.0f / (float)p.cpg;
@@ -149,9 +164,34 @@ __global__ void __launch_bounds__(kSlabThreads) gn_slab_kernel(const SlabParams 
         }
       for (int o = L >> 1; o > 0; o >>= 1) dv += __shfl_xor_sync(0xffffffffu, dv, o);
       if (l == 0 && g < p.S) {
-        const float var = fmaf((float)rows, dv, sq) / ((float)rows * (float)p.cpg);
-        s_fin[g] = make_float2(gmean, rsqrtf(var + p.eps));
+        const float m2 = fmaf((float)rows, dv, sq);
+        if (R == 1) {
+          s_fin[g] = make_float2(gmean, rsqrtf(m2 / ((float)rows * (float)p.cpg) + p.eps));
+        } else {  // push this CTA's (mean, M2) into slot [rank][g] of every CTA of the cluster (DSMEM)
+          for (int pr = 0; pr < R; ++pr) {
+            const uint32_t dst = mapa_u32(&s_x[rank * p.S + g], (uint32_t)pr);
+            asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(dst), "f"(gmean), "f"(m2) : "memory");
+          }
+        }
       }
+    }
+  }
+  if (R > 1) {
+    cluster_sync_all();  // release / acquire: all partials have landed; no remote access happens after this point
+    for (int g = tid; g < p.S; g += kSlabThreads) {  // rank order, double: deterministic and identical in every CTA
+      double tn = 0, tm = 0, tmm = 0, tq = 0;
+      for (int pr = 0; pr < R; ++pr) {
+        const double nk = (double)min(p.rows_per, p.dom_rows - pr * p.rows_per) * p.cpg;
+        const float2 v = s_x[pr * p.S + g];
+        tn += nk;
+        tm += nk * (double)v.x;
+        tmm += nk * (double)v.x * (double)v.x;
+        tq += (double)v.y;
+      }
+      const double mean = tm / tn;
+      double var = (tq + tmm - tn * mean * mean) / tn;
+      if (var < 0) var = 0;
+      s_fin[g] = make_float2((float)mean, rsqrtf((float)var + p.eps));
     }
   }
   __syncthreads();
@@ -202,43 +242,65 @@ __global__ void __launch_bounds__(kSlabThreads) gn_slab_kernel(const SlabParams 
 }
 
 struct SlabPlan {
-  int domains, rows, S, seg_c, nvs, k, gl, slabs_per_dom;
+  int domains, rows, S, seg_c, nvs, k, gl, slabs_per_dom, R, rows_per;
   size_t smem;
 };
 
 bool make_slab_plan(int b, int c, int f, int h, int w, int groups, int per_frame, int dtype, SlabPlan* pl) {
   static const int on = [] { const char* e = getenv("CA_GN_SLAB"); return (e && e[0] == '0') ? 0 : 1; }();
+  // r01d sweep: one CTA per (domain, slab) with slabs up to 96 KB beats both the slice ring and the clustered split wherever it
+  // fits (32x32: 32.7 us vs 40 / 37.6); where it does not (64x64: 327 KB) clusters of 4 / 8 measured 62 / 70 us against the
+  // ring's 60, so the clustered split is opt-in (CA_GN_SLAB_CLUSTER=2/4/8) and the ring keeps those shapes
+  static const int max_r = [] { const char* e = getenv("CA_GN_SLAB_CLUSTER"); const int v = (e && e[0]) ? atoi(e) : 1; return v < 1 ? 1 : (v > kMaxCluster ? kMaxCluster : v); }();
   if (!on) return false;
   if (dtype != CA_BF16 && dtype != CA_F16) return false;
   if (c % kVecE != 0 || groups <= 0 || c % groups != 0) return false;
   const int cpg = c / groups;
   const long long rows = per_frame ? (long long)h * w : (long long)f * h * w;
   const long long domains = per_frame ? (long long)b * f : b;
-  if (rows <= 0 || rows > 4096 || domains <= 0 || domains * groups >= (1ll << 31)) return false;
-  // groups per slab: S | groups, slab rows 16-byte granular and >= 64 B, whole slab in smem; prefer the largest S that still
-  // gives two CTAs per SM, else the smallest valid S
-  const long long want = 2ll * sm_count();
-  int best = 0;
-  for (int S = 1; S <= groups; ++S) {
-    if (groups % S) continue;
-    const long long seg_c = (long long)S * cpg;
-    if (seg_c % kVecE || seg_c * 2 < 64 || seg_c / kVecE > kSlabThreads) continue;
-    if ((size_t)(rows * seg_c * 2) > kSlabTileCap) break;
-    if (best == 0 || domains * (groups / S) >= want) best = S;
+  if (rows <= 0 || rows >= (1 << 20) || domains <= 0 || domains * groups * kMaxCluster >= (1ll << 31)) return false;
+  // groups per slab: S | groups, slab rows 16-byte granular and >= 64 B.  Start from the smallest such S, split the rows over
+  // a cluster of R CTAs until the per-CTA slab is ~40 KB; with R == 1 widen S while the slab stays small and the grid large
+  int S = 0;
+  for (int t = 1; t <= groups; ++t) {
+    if (groups % t) continue;
+    const long long seg = (long long)t * cpg;
+    if (seg % kVecE || seg * 2 < 64) continue;
+    if (seg / kVecE > kSlabThreads) return false;
+    S = t;
+    break;
   }
-  if (best == 0) return false;
+  if (S == 0) return false;
+  int R = 1;
+  while (R < max_r && (size_t)((rows + R - 1) / R) * S * cpg * 2 > kSlabTileTarget) R *= 2;
+  if (R > 1 && rows < 8 * R) return false;
+  long long rows_per = (rows + R - 1) / R;
+  if ((rows + rows_per - 1) / rows_per != R) return false;  // every CTA of the cluster must own at least one row
+  if ((size_t)rows_per * S * cpg * 2 > kSlabTileCap) return false;
+  if (R == 1) {
+    const long long want = 2ll * sm_count();
+    for (int t = S + 1; t <= groups; ++t) {
+      if (groups % t) continue;
+      const long long seg = (long long)t * cpg;
+      if (seg % kVecE || seg / kVecE > kSlabThreads) continue;
+      if ((size_t)(rows * seg * 2) > kSlabTileTarget || domains * (groups / t) < want) break;
+      S = t;
+    }
+  }
   pl->domains = (int)domains;
   pl->rows = (int)rows;
-  pl->S = best;
-  pl->seg_c = best * cpg;
+  pl->S = S;
+  pl->seg_c = S * cpg;
   pl->nvs = pl->seg_c / kVecE;
   pl->k = kSlabThreads / pl->nvs;
   pl->gl = 1;
-  while (pl->gl < 32 && pl->gl * 2 <= cpg && pl->gl * 2 * best <= kSlabThreads) pl->gl *= 2;
-  pl->slabs_per_dom = groups / best;
-  pl->smem = (size_t)rows * pl->seg_c * 2 + sizeof(float) * ((size_t)pl->k * 2 * pl->seg_c + 2 * (size_t)pl->seg_c) +
-             sizeof(float2) * (size_t)best;
-  return pl->smem <= 100 * 1024;
+  while (pl->gl < 32 && pl->gl * 2 <= cpg && pl->gl * 2 * S <= kSlabThreads) pl->gl *= 2;
+  pl->slabs_per_dom = groups / S;
+  pl->R = R;
+  pl->rows_per = (int)rows_per;
+  pl->smem = (size_t)rows_per * pl->seg_c * 2 + sizeof(float) * ((size_t)pl->k * 2 * pl->seg_c + 2 * (size_t)pl->seg_c) +
+             sizeof(float2) * (size_t)S * (1 + R);
+  return pl->smem <= 110 * 1024;
 }
 
 }  // namespace
@@ -254,13 +316,25 @@ int gn_slab_launch(const void* x, void* y, const float* gamma, const float* beta
   p.x = x; p.y = y; p.gamma = gamma; p.beta = beta; p.temb = temb; p.temb_ld = temb_ld;
   p.c = c; p.groups = groups; p.cpg = c / groups;
   p.S = pl.S; p.seg_c = pl.seg_c; p.nvs = pl.nvs; p.k = pl.k; p.gl = pl.gl; p.slabs_per_dom = pl.slabs_per_dom;
-  p.per_frame = per_frame ? 1 : 0; p.f = f; p.eps = eps; p.dom_rows = pl.rows;
+  p.per_frame = per_frame ? 1 : 0; p.f = f; p.eps = eps; p.dom_rows = pl.rows; p.R = pl.R; p.rows_per = pl.rows_per;
   const void* fn = nullptr;
   if (dtype == CA_BF16) fn = apply_silu ? (const void*)gn_slab_kernel<__nv_bfloat16, true> : (const void*)gn_slab_kernel<__nv_bfloat16, false>;
   else fn = apply_silu ? (const void*)gn_slab_kernel<__half, true> : (const void*)gn_slab_kernel<__half, false>;
   CA_CUDA(ensure_dynamic_smem(fn, pl.smem));
   void* args[] = {(void*)&p};
-  CA_CUDA(cudaLaunchKernel(fn, dim3((unsigned)((long long)pl.domains * pl.slabs_per_dom)), dim3(kSlabThreads), args, pl.smem, st));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((long long)pl.domains * pl.slabs_per_dom * pl.R));
+  cfg.blockDim = dim3(kSlabThreads);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)pl.R;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pl.R > 1 ? 1 : 0;
+  CA_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
   *handled = true;
   return CA_OK;
 }

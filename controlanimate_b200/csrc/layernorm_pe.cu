@@ -123,6 +123,100 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 }
 
 
+// ---- flat variant (16-bit storage): no persistence, no ring.  One row group per sub-warp, one pass, exit: the block
+// scheduler keeps many short-lived CTAs at different phases on every SM, which is what makes the plain elementwise
+// epilogue kernel reach 78 % of the copy roofline in the same harness (profiles/r01d_notes.md §7).  The row is kept as raw
+// 16-byte vectors (NV registers x 4) and unpacked per pass so that 4 CTAs x 8 warps fit the register file.
+template <typename T, int LPR, int NV>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
+    layernorm_flat_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          const float* __restrict__ pe, long long rows, int c, int f, int d, float eps) {
+  constexpr int VEC = 8;
+  constexpr int R = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, sl = lane % LPR;
+  const int nvec = c / VEC;
+  const long long row = ((long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * R + sub;
+  const bool live = row < rows;
+  const float inv_c = 1.0f / (float)c;
+  uint4 raw[NV];
+  const T* xr = x + row * c;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = sl + i * LPR;
+    raw[i] = (live && vi < nvec) ? ldg_stream(xr + vi * VEC) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float2 v[4];
+    unpack2(raw[i].x, v[0].x, v[0].y, T());
+    unpack2(raw[i].y, v[1].x, v[1].y, T());
+    unpack2(raw[i].z, v[2].x, v[2].y, T());
+    unpack2(raw[i].w, v[3].x, v[3].y, T());
+    sum2 = __fadd2_rn(sum2, __fadd2_rn(__fadd2_rn(v[0], v[1]), __fadd2_rn(v[2], v[3])));
+  }
+  float sum = sum2.x + sum2.y;
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * inv_c;
+  const float2 nmean = make_float2(-mean, -mean);
+  float2 sq2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (sl + i * LPR < nvec) {
+      float2 v[4];
+      unpack2(raw[i].x, v[0].x, v[0].y, T());
+      unpack2(raw[i].y, v[1].x, v[1].y, T());
+      unpack2(raw[i].z, v[2].x, v[2].y, T());
+      unpack2(raw[i].w, v[3].x, v[3].y, T());
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 dl = __fadd2_rn(v[j], nmean);
+        sq2 = __ffma2_rn(dl, dl, sq2);
+      }
+    }
+  }
+  float sq = sq2.x + sq2.y;
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq * inv_c + eps);
+  if (!live) return;
+  const float2 rstd2 = make_float2(rstd, rstd), nmr2 = make_float2(-mean * rstd, -mean * rstd);
+  const float* per = pe ? pe + (long long)((row / d) % f) * c : nullptr;
+  T* yr = y + row * c;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = sl + i * LPR;
+    if (vi < nvec) {
+      float2 v[4], o[4];
+      unpack2(raw[i].x, v[0].x, v[0].y, T());
+      unpack2(raw[i].y, v[1].x, v[1].y, T());
+      unpack2(raw[i].z, v[2].x, v[2].y, T());
+      unpack2(raw[i].w, v[3].x, v[3].y, T());
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + vi * VEC + 4 * j));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + vi * VEC + 4 * j));
+        float2 b01 = make_float2(b4.x, b4.y), b23 = make_float2(b4.z, b4.w);
+        if (per) {
+          const float4 p4 = __ldg(reinterpret_cast<const float4*>(per + vi * VEC + 4 * j));
+          b01 = __fadd2_rn(b01, make_float2(p4.x, p4.y));
+          b23 = __fadd2_rn(b23, make_float2(p4.z, p4.w));
+        }
+        o[2 * j] = __ffma2_rn(__ffma2_rn(v[2 * j], rstd2, nmr2), make_float2(g4.x, g4.y), b01);
+        o[2 * j + 1] = __ffma2_rn(__ffma2_rn(v[2 * j + 1], rstd2, nmr2), make_float2(g4.z, g4.w), b23);
+      }
+      uint4 out;
+      out.x = pack2(o[0].x, o[0].y, T());
+      out.y = pack2(o[1].x, o[1].y, T());
+      out.z = pack2(o[2].x, o[2].y, T());
+      out.w = pack2(o[3].x, o[3].y, T());
+      stg_stream(yr + vi * VEC, out);
+    }
+  }
+}
+
 // ---- pipelined variant (16-bit storage): rows travel HBM -> smem by bulk async copies, registers hold one row only ----
 // The register-resident kernel above keeps at most two rows of loads in flight per warp and, at ~100 registers per
 // thread, 16 warps per SM: ~40 KB outstanding per SM, measured 46 % of the copy roofline at c = 320
@@ -326,10 +420,38 @@ extern "C" __attribute__((visibility("default"))) int ca_layernorm_pe(const void
   while (lpr < 32 && (nvec + lpr - 1) / lpr > 5) lpr <<= 1;
   const int nv = (nvec + lpr - 1) / lpr;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static const int ln_mode = [] { const char* e = getenv("CA_LN_MODE"); return !e ? 0 : (e[0] == 'f' ? 1 : (e[0] == 'r' ? 2 : (e[0] == 'p' ? 3 : 0))); }();
+  // 0 auto, 1 flat (non-persistent), 2 ring, 3 persistent register-resident
+  if ((ln_mode == 1 || ln_mode == 0) && dtype != CA_F32 && nv <= 5 && aligned16(gamma) && aligned16(beta)) {
+    const int rc2 = dispatch_dtype(dtype, [&](auto tag) -> int {
+      using T = decltype(tag);
+      if constexpr (sizeof(T) == 2) {
+        auto run = [&](auto kernel) -> int {
+          const int rows_per_cta = kWarpsPerCta * (32 / lpr);
+          const long long grid = (rows + rows_per_cta - 1) / rows_per_cta;
+          if (grid >= (1ll << 31)) return CA_ERR_UNSUPPORTED;
+          kernel<<<(unsigned)grid, kWarpsPerCta * 32, 0, st>>>(reinterpret_cast<const T*>(x), reinterpret_cast<T*>(y), gamma, beta, pe,
+                                                               rows, c, f, d, eps);
+          return CA_OK;
+        };
+#define CA_LNF_CASE(L_, N_) if (lpr == L_ && nv <= N_) return run(layernorm_flat_kernel<T, L_, N_>)
+        CA_LNF_CASE(8, 1); CA_LNF_CASE(8, 2); CA_LNF_CASE(8, 3); CA_LNF_CASE(8, 5);
+        CA_LNF_CASE(16, 3); CA_LNF_CASE(16, 5);
+        CA_LNF_CASE(32, 3); CA_LNF_CASE(32, 5);
+#undef CA_LNF_CASE
+      }
+      return CA_ERR_UNSUPPORTED;
+    });
+    if (rc2 == CA_OK) {
+      CA_CUDA(cudaGetLastError());
+      return CA_OK;
+    }
+    if (rc2 != CA_ERR_UNSUPPORTED) return rc2;
+  }
   static const int ring_on = [] { const char* e = getenv("CA_LN_RING"); return (e && e[0] == '0') ? 0 : 1; }();
   static const int ring_kb = [] { const char* e = getenv("CA_LN_RING_KB"); return (e && e[0]) ? atoi(e) : 20; }();
   static const int ring_stages = [] { const char* e = getenv("CA_LN_RING_STAGES"); return (e && e[0]) ? atoi(e) : 4; }();
-  if (ring_on && dtype != CA_F32 && nv <= 5) {
+  if (ring_on && ln_mode != 3 && dtype != CA_F32 && nv <= 5) {
     // pipelined path: tiles of whole row groups (kLnRingWarps * 32/lpr rows), about ring_kb KB each
     const int group = kLnRingWarps * (32 / lpr);
     const long long row_bytes = (long long)c * 2;

@@ -50,7 +50,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--out", default="gpurun_out/microbench.json")
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--only", default="", help="comma list of kernel families: gn,ln,attn,xattn,gemm,merge")
+    ap.add_argument("--only", default="", help="comma list of kernel families: gn,ln,attn,xattn,copy,gemm,merge")
     args = ap.parse_args()
     only = set(filter(None, args.only.split(",")))
     want = lambda fam: not only or fam in only  # noqa: E731
@@ -91,6 +91,15 @@ def main():
                 y = torch.empty_like(inp)
                 us, mn = timeit(lambda: ops.groupnorm_silu(inp, g, be, 32, 1e-5, temb=te, out=y), args.iters, flush)
                 add("groupnorm_silu", f"b{b} c{c} f{f} {s}x{s} {name} +temb", us, mn, 2.0 * n * 2)
+            if want("copy"):
+                # yardsticks on the same tensor and the same timing harness: a plain device copy and the elementwise conv epilogue
+                y = torch.empty_like(xn)
+                us, mn = timeit(lambda: y.copy_(xn), args.iters, flush)
+                add("torch_copy(yardstick)", f"b{b} c{c} f{f} {s}x{s}", us, mn, 2.0 * n * 2)
+                x4 = xn.permute(0, 2, 1, 3, 4).reshape(b * f, c, s, s)
+                bz = te[0].contiguous()
+                us, mn = timeit(lambda: ops.bias_act_residual(x4, bz, silu=True, inplace=True), args.iters, flush)
+                add("bias_act_residual(silu)", f"n{b * f} c{c} {s}x{s}", us, mn, 2.0 * n * 2)
             # LayerNorm + PE on tokens
             tok = xn.permute(0, 2, 3, 4, 1).reshape(-1, c)
             pe = torch.randn(32, c, device=dev)

@@ -85,9 +85,9 @@ def test_groupnorm_silu(ops, case, layout, dtype):
         assert relerr(y, ref) <= REL[dtype], (case, layout, dtype, silu)
 
 
-@pytest.mark.parametrize("env", [{"CA_GN_SLAB": "0"}, {"CA_GN_SLAB": "0", "CA_GN_STREAM": "1"}, {"CA_GN_SLAB": "0", "CA_GN_RING": "0"},
-                                 {"CA_GN_SLAB": "0", "CA_GN_RING": "0", "CA_GN_TEAM": "0"}],
-                         ids=["ring", "stream-pair", "team", "split"])
+@pytest.mark.parametrize("env", [{"CA_GN_SLAB": "0"}, {"CA_GN_SLAB_CLUSTER": "8"}, {"CA_GN_SLAB": "0", "CA_GN_STREAM": "1"},
+                                 {"CA_GN_SLAB": "0", "CA_GN_RING": "0"}, {"CA_GN_SLAB": "0", "CA_GN_RING": "0", "CA_GN_TEAM": "0"}],
+                         ids=["ring", "slab-clusters", "stream-pair", "team", "split"])
 def test_groupnorm_alternative_paths(env):
     """The native-layout GroupNorm picks among several kernels behind ca_groupnorm_silu (small-domain slab kernel, slice ring,
     streaming pair, team kernel, split launches); the path is chosen once per process from the environment, so the ones the
@@ -215,6 +215,21 @@ X_CASES = [
     (2, 256, 8, 160, 2, 81, False),   # IP-Adapter length (77 + 4 image tokens): 96-key variant, two P V passes
     (3, 130, 4, 40, 1, 5, False),     # very short prompt, one prompt for every frame
 ]
+
+
+@pytest.mark.parametrize("mode", ["ring", "persist"])
+def test_layernorm_alternative_paths(mode):
+    """ca_layernorm_pe defaults to the flat kernel for 16-bit rows; the smem-ring and the persistent register-resident
+    kernels stay selectable (CA_LN_MODE) and are re-checked in child processes against the same oracle cases."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("CA_LN_CHILD") == "1":
+        pytest.skip("already inside a child run")
+    child_env = dict(os.environ, CA_LN_CHILD="1", CA_LN_MODE=mode)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", __file__, "-k",
+                        "layernorm and not alternative"], env=child_env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
