@@ -1,12 +1,14 @@
 // Kernel (2), native-layout streaming path: GroupNorm + SiLU (+ time-embedding add) on a BFHWC video activation as two
 // plain streaming kernels whose second read is served by the 126 MB L2:
 //
-//     statistics : every CTA streams one slice (k*j rows of one statistics domain) HBM -> registers with 8 independent
-//                  16-byte loads per thread in flight, accumulates shifted per-channel sums (packed f32x2), folds them to
-//                  per-group (mean, M2) and writes one 8-byte partial per (domain, slice, group)
-//     normalise  : every CTA folds the partials of its domain (slice order, double: deterministic), then re-reads its
-//                  slice -- domains are walked in REVERSE order of the statistics launch, so the most recently read
-//                  lines are still L2-resident -- and writes y with streaming (evict-first) stores that do not displace x
+//     statistics : flat grid, one short-lived CTA per slice (k*8 rows of one statistics domain): every thread has all 8 of
+//                  its 16-byte loads in flight at once, accumulates per-channel sums shifted by its OWN first row (packed
+//                  f32x2; no load depends on another), the row lanes are merged with Chan's formula, channels folded to
+//                  per-group (mean, M2): one 8-byte partial per (domain, slice, group)
+//     finalize   : one CTA per domain folds the partials (slice order, double: deterministic) -> (mean, rstd) per group
+//     normalise  : flat grid again, domains walked in REVERSE order of the statistics launch, so the most recently read
+//                  lines are still L2-resident; loads first, then the per-channel scale / shift, then streaming
+//                  (evict-first) stores that do not displace x
 //
 // HBM traffic stays at the algorithmic 2*N*s bytes (one read + one write) as long as the chunk of domains handed to the
 // pair of launches fits the L2; larger tensors are cut into chunks of whole domains on the host (domains are independent).
@@ -14,11 +16,11 @@
 // Replaces InflatedGroupNorm.forward + F.silu (reference animatediff/models/resnet.py:23-31, 191-192, 199-208;
 // unet.py:614-615) and the transformer-entry GroupNorms (motion_module.py:144, attention.py:131).
 //
-// Status: an ALTERNATIVE to groupnorm_ring.cu, off by default (CA_GN_STREAM=1 selects it).  The idea -- two exchange-free
-// streaming kernels instead of a cross-CTA statistics exchange -- was measured in r01d (profiles/r01d_notes.md): 72.7 us
-// at c320 64x64 against 59 us for the slice ring, and a fixed ~60 us on the small levels where the per-CTA fold of the
-// partials dominates, so the ring stays the product path.  Kept because the L2-resident re-read is the right shape for a
-// future variant with persistent CTAs and a separate finalize launch.
+// Status: an ALTERNATIVE to groupnorm_ring.cu / groupnorm_slab.cu, off by default (CA_GN_STREAM=1 selects it), kept as the
+// measured record of the "exchange-free flat launches" idea (profiles/r01d_notes.md §1, §7): 86.7 us at c320 64x64 in this
+// form (72.7 us in a first form with 16 rows per thread and the fold inside the normalise CTAs) against 60 us for the slice
+// ring.  The per-CTA statistics epilogue and the per-thread scale/shift prologue cost as many issue slots as the 8 rows a
+// thread streams, so the two passes run at about half the speed of the plain elementwise epilogue kernel they imitate.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -46,6 +48,7 @@ struct StreamParams {
   int dom_rows, slice_rows, spd;
   int dom0, ndom;           // this launch covers domains [dom0, dom0 + ndom)
   float2* partials;         // [domains][spd][groups] (mean, M2)
+  float2* finals;           // [domains][groups] (mean, rstd)
 };
 
 __device__ __forceinline__ float tanh_fast_s(float v) {
@@ -66,8 +69,8 @@ template <typename T>
 __global__ void __launch_bounds__(kSThreads) gn_stream_stats_kernel(const StreamParams p) {
   extern __shared__ __align__(16) float s_dyn[];
   const int Cs = p.cs, nvec = p.nvec, k = p.k;
-  float* s_part = s_dyn;                        // [k][2][Cs]
-  float* s_ch = s_part + (size_t)k * 2 * Cs;    // [2][Cs]
+  float* s_part = s_dyn;                        // [k][3][Cs]: x0 (the lane's own shift), sum(x - x0), sum((x - x0)^2)
+  float* s_ch = s_part + (size_t)k * 3 * Cs;    // [2][Cs]
   const int tid = threadIdx.x;
   const int slab = blockIdx.y;
   const int dl = blockIdx.x / p.spd, sl = blockIdx.x - dl * p.spd;
@@ -77,68 +80,74 @@ __global__ void __launch_bounds__(kSThreads) gn_stream_stats_kernel(const Stream
   const int bi = p.per_frame ? dom / p.f : dom;
   const bool on = tid < nvec * k;
   const int cv = tid % nvec, rl = tid / nvec;
-  const T* xs = reinterpret_cast<const T*>(p.x) + ((long long)dom * p.dom_rows + r0) * p.c + (long long)slab * Cs;
+  const T* xt = reinterpret_cast<const T*>(p.x) + ((long long)dom * p.dom_rows + r0) * p.c + (long long)slab * Cs + cv * kVecE;
 
   if (on) {
-    float2 nx0[4], s1[4], s2[4];
-    {
-      const uint4 v0 = ldg_l2_keep(xs + cv * kVecE);  // the slice's first row: the shift every row lane shares
-      unpack2(v0.x, nx0[0].x, nx0[0].y, T());
-      unpack2(v0.y, nx0[1].x, nx0[1].y, T());
-      unpack2(v0.z, nx0[2].x, nx0[2].y, T());
-      unpack2(v0.w, nx0[3].x, nx0[3].y, T());
+    // slice_rows = k * kBatch: every load of this thread is in flight at once; the shift is the thread's OWN first row, so no
+    // load depends on another (row lanes are merged with Chan's formula below)
+    uint4 raw[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int r = rl + u * k;
+      raw[u] = r < rows ? ldg_l2_keep(xt + (long long)r * p.c) : make_uint4(0u, 0u, 0u, 0u);
     }
+    float2 x0[4], s1[4], s2[4];
+    unpack2(raw[0].x, x0[0].x, x0[0].y, T());
+    unpack2(raw[0].y, x0[1].x, x0[1].y, T());
+    unpack2(raw[0].z, x0[2].x, x0[2].y, T());
+    unpack2(raw[0].w, x0[3].x, x0[3].y, T());
+    float2 nx0[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      nx0[e] = make_float2(-nx0[e].x, -nx0[e].y);
+      nx0[e] = make_float2(-x0[e].x, -x0[e].y);
       s1[e] = s2[e] = make_float2(0.f, 0.f);
     }
-    const T* xt = xs + cv * kVecE;
-    for (int rb = rl; rb < rows; rb += k * kBatch) {
-      uint4 raw[kBatch];
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        const int r = rb + u * k;
-        raw[u] = r < rows ? ldg_l2_keep(xt + (long long)r * p.c) : make_uint4(0u, 0u, 0u, 0u);
-      }
+    for (int u = 1; u < kBatch; ++u) {
+      if (rl + u * k < rows) {
+        float2 v[4];
+        unpack2(raw[u].x, v[0].x, v[0].y, T());
+        unpack2(raw[u].y, v[1].x, v[1].y, T());
+        unpack2(raw[u].z, v[2].x, v[2].y, T());
+        unpack2(raw[u].w, v[3].x, v[3].y, T());
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        if (rb + u * k < rows) {
-          float2 v[4];
-          unpack2(raw[u].x, v[0].x, v[0].y, T());
-          unpack2(raw[u].y, v[1].x, v[1].y, T());
-          unpack2(raw[u].z, v[2].x, v[2].y, T());
-          unpack2(raw[u].w, v[3].x, v[3].y, T());
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 d = __fadd2_rn(v[e], nx0[e]);
-            s1[e] = __fadd2_rn(s1[e], d);
-            s2[e] = __ffma2_rn(d, d, s2[e]);
-          }
+        for (int e = 0; e < 4; ++e) {
+          const float2 d = __fadd2_rn(v[e], nx0[e]);
+          s1[e] = __fadd2_rn(s1[e], d);
+          s2[e] = __ffma2_rn(d, d, s2[e]);
         }
       }
     }
-    float4* d1 = reinterpret_cast<float4*>(s_part + ((size_t)rl * 2 + 0) * Cs + cv * kVecE);
-    float4* d2 = reinterpret_cast<float4*>(s_part + ((size_t)rl * 2 + 1) * Cs + cv * kVecE);
+    float4* d0 = reinterpret_cast<float4*>(s_part + ((size_t)rl * 3 + 0) * Cs + cv * kVecE);
+    float4* d1 = reinterpret_cast<float4*>(s_part + ((size_t)rl * 3 + 1) * Cs + cv * kVecE);
+    float4* d2 = reinterpret_cast<float4*>(s_part + ((size_t)rl * 3 + 2) * Cs + cv * kVecE);
+    d0[0] = make_float4(x0[0].x, x0[0].y, x0[1].x, x0[1].y);
+    d0[1] = make_float4(x0[2].x, x0[2].y, x0[3].x, x0[3].y);
     d1[0] = make_float4(s1[0].x, s1[0].y, s1[1].x, s1[1].y);
     d1[1] = make_float4(s1[2].x, s1[2].y, s1[3].x, s1[3].y);
     d2[0] = make_float4(s2[0].x, s2[0].y, s2[1].x, s2[1].y);
     d2[1] = make_float4(s2[2].x, s2[2].y, s2[3].x, s2[3].y);
   }
   __syncthreads();
-  {  // per-channel (mean, M2) of the slice: the row lanes share the shift, so their sums just add (fixed order)
-    const float inv_n = 1.0f / (float)rows;
+  {  // per-channel (mean, M2) of the slice: Chan merge of the row lanes in lane order (fixed order: deterministic)
     const float* tp = p.temb ? p.temb + (long long)bi * p.temb_ld + (long long)slab * Cs : nullptr;
     for (int c0 = tid; c0 < Cs; c0 += kSThreads) {
-      float a1 = 0.f, a2 = 0.f;
+      float n = 0.f, mean = 0.f, m2 = 0.f;
       for (int q = 0; q < k; ++q) {
-        a1 += s_part[((size_t)q * 2 + 0) * Cs + c0];
-        a2 += s_part[((size_t)q * 2 + 1) * Cs + c0];
+        const int nq_i = q < rows ? (rows - q + k - 1) / k : 0;
+        if (nq_i == 0) break;
+        const float nq = (float)nq_i;
+        const float a1 = s_part[((size_t)q * 3 + 1) * Cs + c0], a2 = s_part[((size_t)q * 3 + 2) * Cs + c0];
+        const float dm = a1 / nq;
+        const float mq = s_part[((size_t)q * 3 + 0) * Cs + c0] + dm;
+        const float m2q = fmaxf(a2 - a1 * dm, 0.f);
+        const float nt = n + nq, delta = mq - mean;
+        mean += delta * (nq / nt);
+        m2 += m2q + delta * delta * (n * nq / nt);
+        n = nt;
       }
-      const float t = tp ? __ldg(tp + c0) : 0.f;
-      const float dm = a1 * inv_n;
-      s_ch[c0] = Traits<T>::to_f(xs[c0]) + t + dm;
-      s_ch[Cs + c0] = fmaxf(a2 - a1 * dm, 0.f);
+      s_ch[c0] = mean + (tp ? __ldg(tp + c0) : 0.f);
+      s_ch[Cs + c0] = m2;
     }
   }
   __syncthreads();
@@ -172,12 +181,52 @@ __global__ void __launch_bounds__(kSThreads) gn_stream_stats_kernel(const Stream
   }
 }
 
+// one CTA per domain: fold the slice partials in slice order, double (deterministic) -> (mean, rstd) per group
+__global__ void __launch_bounds__(kSThreads) gn_stream_finalize_kernel(const StreamParams p) {
+  __shared__ double s_fold[4][8][33];
+  const int dom = p.dom0 + blockIdx.x;
+  const int tid = threadIdx.x, lane_q = tid >> 5, lane_g = tid & 31;
+  const float2* part = p.partials + (long long)dom * p.spd * p.groups;
+  for (int g0 = 0; g0 < p.groups; g0 += 32) {
+    const int g = g0 + lane_g;
+    double a_n = 0, a_m = 0, a_mm = 0, a_q = 0;
+    if (g < p.groups) {
+#pragma unroll 4
+      for (int q = lane_q; q < p.spd; q += 8) {
+        const float2 v = __ldcg(part + (long long)q * p.groups + g);
+        const double nk = (double)(min(p.slice_rows, p.dom_rows - q * p.slice_rows)) * p.cpg;
+        const double m = (double)v.x;
+        a_n += nk;
+        a_m += nk * m;
+        a_mm += nk * m * m;
+        a_q += (double)v.y;
+      }
+    }
+    s_fold[0][lane_q][lane_g] = a_n;
+    s_fold[1][lane_q][lane_g] = a_m;
+    s_fold[2][lane_q][lane_g] = a_mm;
+    s_fold[3][lane_q][lane_g] = a_q;
+    __syncthreads();
+    if (lane_q == 0 && g < p.groups) {
+      double tn = 0, tm = 0, tmm = 0, tq = 0;
+      for (int l = 0; l < 8; ++l) {
+        tn += s_fold[0][l][lane_g];
+        tm += s_fold[1][l][lane_g];
+        tmm += s_fold[2][l][lane_g];
+        tq += s_fold[3][l][lane_g];
+      }
+      const double mean = tm / tn;
+      double var = (tq + tmm - tn * mean * mean) / tn;
+      if (var < 0) var = 0;
+      p.finals[(long long)dom * p.groups + g] = make_float2((float)mean, rsqrtf((float)var + p.eps));
+    }
+    __syncthreads();
+  }
+}
+
 template <typename T, bool kSilu>
 __global__ void __launch_bounds__(kSThreads) gn_stream_apply_kernel(const StreamParams p) {
-  extern __shared__ __align__(16) float s_dyn[];
   const int Cs = p.cs, nvec = p.nvec, k = p.k;
-  double* s_fold = reinterpret_cast<double*>(s_dyn);                       // [4][8][33]
-  float2* s_fin = reinterpret_cast<float2*>(s_fold + 4 * 8 * 33);          // [gs] (mean, rstd)
   const int tid = threadIdx.x;
   const int slab = blockIdx.y;
   // reverse domain order: the statistics launch read domain ndom-1 last, so it is the most likely to still be in L2
@@ -186,70 +235,26 @@ __global__ void __launch_bounds__(kSThreads) gn_stream_apply_kernel(const Stream
   const int r0 = sl * p.slice_rows;
   const int rows = min(p.slice_rows, p.dom_rows - r0);
   const int bi = p.per_frame ? dom / p.f : dom;
-  const bool on = tid < nvec * k;
+  if (tid >= nvec * k) return;
   const int cv = tid % nvec, rl = tid / nvec;
-  const T* xt = reinterpret_cast<const T*>(p.x) + ((long long)dom * p.dom_rows + r0) * p.c + (long long)slab * Cs + cv * kVecE;
-  T* yt = reinterpret_cast<T*>(p.y) + ((long long)dom * p.dom_rows + r0) * p.c + (long long)slab * Cs + cv * kVecE;
+  const long long co = (long long)slab * Cs + cv * kVecE;
+  const T* xt = reinterpret_cast<const T*>(p.x) + ((long long)dom * p.dom_rows + r0) * p.c + co;
+  T* yt = reinterpret_cast<T*>(p.y) + ((long long)dom * p.dom_rows + r0) * p.c + co;
 
-  // the first batch of rows is requested before the statistics are folded: its L2 latency hides behind the fold
+  // all rows of this thread are requested before the per-channel scale / shift is assembled (its L2 round trip hides behind them)
   uint4 raw[kBatch];
-  if (on) {
 #pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const int r = rl + u * k;
-      raw[u] = r < rows ? ldg_stream(xt + (long long)r * p.c) : make_uint4(0u, 0u, 0u, 0u);
-    }
+  for (int u = 0; u < kBatch; ++u) {
+    const int r = rl + u * k;
+    raw[u] = r < rows ? ldg_stream(xt + (long long)r * p.c) : make_uint4(0u, 0u, 0u, 0u);
   }
-
-  {  // fold the domain's slice partials in slice order, double: N, sum n*m, sum n*m^2, sum M2 (deterministic)
-    const float2* part = p.partials + (long long)dom * p.spd * p.groups + slab * p.gs;
-    const int lane_q = tid >> 5, lane_g = tid & 31;
-    for (int g0 = 0; g0 < p.gs; g0 += 32) {
-      const int g = g0 + lane_g;
-      double a_n = 0, a_m = 0, a_mm = 0, a_q = 0;
-      if (g < p.gs) {
-#pragma unroll 4
-        for (int q = lane_q; q < p.spd; q += 8) {
-          const float2 v = __ldcg(part + (long long)q * p.groups + g);
-          const double nk = (double)(min(p.slice_rows, p.dom_rows - q * p.slice_rows)) * p.cpg;
-          const double m = (double)v.x;
-          a_n += nk;
-          a_m += nk * m;
-          a_mm += nk * m * m;
-          a_q += (double)v.y;
-        }
-      }
-      s_fold[(0 * 8 + lane_q) * 33 + lane_g] = a_n;
-      s_fold[(1 * 8 + lane_q) * 33 + lane_g] = a_m;
-      s_fold[(2 * 8 + lane_q) * 33 + lane_g] = a_mm;
-      s_fold[(3 * 8 + lane_q) * 33 + lane_g] = a_q;
-      __syncthreads();
-      if (lane_q == 0 && g < p.gs) {
-        double tn = 0, tm = 0, tmm = 0, tq = 0;
-        for (int l = 0; l < 8; ++l) {
-          tn += s_fold[(0 * 8 + l) * 33 + lane_g];
-          tm += s_fold[(1 * 8 + l) * 33 + lane_g];
-          tmm += s_fold[(2 * 8 + l) * 33 + lane_g];
-          tq += s_fold[(3 * 8 + l) * 33 + lane_g];
-        }
-        const double mean = tm / tn;
-        double var = (tq + tmm - tn * mean * mean) / tn;
-        if (var < 0) var = 0;
-        s_fin[g] = make_float2((float)mean, rsqrtf((float)var + p.eps));
-      }
-      __syncthreads();
-    }
-  }
-  if (!on) return;
-
   float2 av[4], bv[4];
   {
-    const long long co = (long long)slab * Cs + cv * kVecE;
-    const int g_first = (cv * kVecE) / p.cpg;
+    const float2* fin = p.finals + (long long)dom * p.groups;
     const float* tp = p.temb ? p.temb + (long long)bi * p.temb_ld + co : nullptr;
 #pragma unroll
     for (int e = 0; e < kVecE; e += 2) {
-      const float2 m0 = s_fin[(cv * kVecE + e) / p.cpg], m1 = s_fin[(cv * kVecE + e + 1) / p.cpg];
+      const float2 m0 = __ldg(fin + (int)((co + e) / p.cpg)), m1 = __ldg(fin + (int)((co + e + 1) / p.cpg));
       float a0 = __ldg(p.gamma + co + e) * m0.y, a1 = __ldg(p.gamma + co + e + 1) * m1.y;
       const float t0 = tp ? __ldg(tp + e) : 0.f, t1 = tp ? __ldg(tp + e + 1) : 0.f;
       float b0 = fmaf(t0 - m0.x, a0, __ldg(p.beta + co + e)), b1 = fmaf(t1 - m1.x, a1, __ldg(p.beta + co + e + 1));
@@ -262,38 +267,28 @@ __global__ void __launch_bounds__(kSThreads) gn_stream_apply_kernel(const Stream
       av[e / 2] = make_float2(a0, a1);
       bv[e / 2] = make_float2(b0, b1);
     }
-    (void)g_first;
   }
-  for (int rb = rl; rb < rows; rb += k * kBatch) {
-    if (rb != rl) {
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        const int r = rb + u * k;
-        raw[u] = r < rows ? ldg_stream(xt + (long long)r * p.c) : make_uint4(0u, 0u, 0u, 0u);
+  for (int u = 0; u < kBatch; ++u) {
+    const int r = rl + u * k;
+    if (r < rows) {
+      float2 v[4];
+      unpack2(raw[u].x, v[0].x, v[0].y, T());
+      unpack2(raw[u].y, v[1].x, v[1].y, T());
+      unpack2(raw[u].z, v[2].x, v[2].y, T());
+      unpack2(raw[u].w, v[3].x, v[3].y, T());
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 hh = __ffma2_rn(v[e], av[e], bv[e]);
+        if constexpr (kSilu) v[e] = __ffma2_rn(hh, make_float2(tanh_fast_s(hh.x), tanh_fast_s(hh.y)), hh);
+        else v[e] = hh;
       }
-    }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const int r = rb + u * k;
-      if (r < rows) {
-        float2 v[4];
-        unpack2(raw[u].x, v[0].x, v[0].y, T());
-        unpack2(raw[u].y, v[1].x, v[1].y, T());
-        unpack2(raw[u].z, v[2].x, v[2].y, T());
-        unpack2(raw[u].w, v[3].x, v[3].y, T());
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 hh = __ffma2_rn(v[e], av[e], bv[e]);
-          if constexpr (kSilu) v[e] = __ffma2_rn(hh, make_float2(tanh_fast_s(hh.x), tanh_fast_s(hh.y)), hh);
-          else v[e] = hh;
-        }
-        uint4 out;
-        out.x = pack2(v[0].x, v[0].y, T());
-        out.y = pack2(v[1].x, v[1].y, T());
-        out.z = pack2(v[2].x, v[2].y, T());
-        out.w = pack2(v[3].x, v[3].y, T());
-        stg_evict_first(yt + (long long)r * p.c, out);
-      }
+      uint4 out;
+      out.x = pack2(v[0].x, v[0].y, T());
+      out.y = pack2(v[1].x, v[1].y, T());
+      out.z = pack2(v[2].x, v[2].y, T());
+      out.w = pack2(v[3].x, v[3].y, T());
+      stg_evict_first(yt + (long long)r * p.c, out);
     }
   }
 }
@@ -309,7 +304,7 @@ int s_env_int(const char* name, int dflt) {
 }
 
 bool make_stream_plan(int b, int c, int f, int h, int w, int groups, int per_frame, int dtype, StreamPlan* pl) {
-  static const int on = s_env_int("CA_GN_STREAM", 0);  // opt-in: r01d measured it slower than the slice ring (73 vs 59 us at c320 64x64)
+  static const int on = s_env_int("CA_GN_STREAM", 0);  // opt-in: r01d measured it slower than the slice ring (see the header)
   static const int rows_per_thread = s_env_int("CA_GN_STREAM_ROWS", 16);
   static const int chunk_mb = s_env_int("CA_GN_STREAM_MB", 96);
   if (!on) return false;
@@ -323,13 +318,9 @@ bool make_stream_plan(int b, int c, int f, int h, int w, int groups, int per_fra
   const long long domains = per_frame ? (long long)b * f : b;
   if (rows <= 0 || rows >= (1ll << 30) || domains <= 0 || domains >= (1ll << 24)) return false;
   const int k = kSThreads / nvec;
-  long long j = rows_per_thread < 1 ? 1 : rows_per_thread;
-  long long slice_rows = (long long)k * j;
+  (void)rows_per_thread;
+  long long slice_rows = (long long)k * kBatch;  // every thread holds all of its rows in registers at once
   if (slice_rows > rows) slice_rows = rows;
-  // enough CTAs to fill the machine a few times over, but slices of at least k rows
-  const long long want_ctas = 8ll * sm_count();
-  while (slice_rows > k && domains * ((rows + slice_rows - 1) / slice_rows) * slabs < want_ctas) slice_rows = (slice_rows + 1) / 2;
-  if (slice_rows < 1) slice_rows = 1;
   const long long spd = (rows + slice_rows - 1) / slice_rows;
   if (spd >= (1ll << 20) || domains * spd >= (1ll << 31)) return false;
   pl->domains = (int)domains;
@@ -344,9 +335,9 @@ bool make_stream_plan(int b, int c, int f, int h, int w, int groups, int per_fra
   if (cd < 1) cd = 1;
   if (cd > domains) cd = domains;
   pl->chunk_domains = (int)cd;
-  pl->smem_stats = sizeof(float) * ((size_t)k * 2 * cs + 2 * (size_t)cs);
-  pl->smem_apply = sizeof(double) * 4 * 8 * 33 + sizeof(float2) * (size_t)gs;
-  pl->partial_bytes = sizeof(float2) * (size_t)domains * spd * groups;
+  pl->smem_stats = sizeof(float) * ((size_t)k * 3 * cs + 2 * (size_t)cs);
+  pl->smem_apply = 0;
+  pl->partial_bytes = sizeof(float2) * ((size_t)domains * spd * groups + (size_t)domains * groups);
   return pl->smem_stats <= 160 * 1024;
 }
 
@@ -374,6 +365,7 @@ int gn_stream_launch(const void* x, void* y, const float* gamma, const float* be
   p.per_frame = per_frame ? 1 : 0; p.f = f; p.eps = eps;
   p.dom_rows = pl.dom_rows; p.slice_rows = pl.slice_rows; p.spd = pl.spd;
   p.partials = reinterpret_cast<float2*>(workspace);
+  p.finals = p.partials + (size_t)pl.domains * pl.spd * groups;
 
   return dispatch_dtype(dtype, [&](auto tag) -> int {
     using T = decltype(tag);
@@ -383,14 +375,14 @@ int gn_stream_launch(const void* x, void* y, const float* gamma, const float* be
       auto stats = gn_stream_stats_kernel<T>;
       const void* apply = apply_silu ? (const void*)gn_stream_apply_kernel<T, true> : (const void*)gn_stream_apply_kernel<T, false>;
       CA_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(stats), pl.smem_stats));
-      CA_CUDA(ensure_dynamic_smem(apply, pl.smem_apply));
       for (int d0 = 0; d0 < pl.domains; d0 += pl.chunk_domains) {
         p.dom0 = d0;
         p.ndom = pl.domains - d0 < pl.chunk_domains ? pl.domains - d0 : pl.chunk_domains;
         const dim3 grid((unsigned)((long long)p.ndom * pl.spd), (unsigned)pl.slabs);
         stats<<<grid, kSThreads, pl.smem_stats, st>>>(p);
+        gn_stream_finalize_kernel<<<(unsigned)p.ndom, kSThreads, 0, st>>>(p);
         void* args[] = {(void*)&p};
-        CA_CUDA(cudaLaunchKernel(apply, grid, dim3(kSThreads), args, pl.smem_apply, st));
+        CA_CUDA(cudaLaunchKernel(apply, grid, dim3(kSThreads), args, 0, st));
       }
       CA_CUDA(cudaGetLastError());
       *handled = true;
