@@ -131,3 +131,31 @@ def test_install_into_unmodified_reference_unet():
                 sys.path.remove(p)
         for m in [m for m in sys.modules if m.split(".")[0] in ("diffusers", "animatediff", "modules", "controlnet_aux")]:
             del sys.modules[m]
+
+
+def test_conv_weight_is_relaid_once_per_version():
+    """layers._weight_cl hands cuDNN a channels_last filter without re-laying it on every call (r01c: 158 copies per step),
+    and notices in-place weight updates (load_state_dict / LoRA merges bump the version counter)."""
+    from controlanimate_b200 import layers
+    conv = torch.nn.Conv2d(8, 16, 3, padding=1, bias=False)
+    w1 = layers._weight_cl(conv)
+    assert w1.is_contiguous(memory_format=torch.channels_last) and torch.equal(w1, conv.weight)
+    assert layers._weight_cl(conv) is w1                                  # cached
+    with torch.no_grad():
+        conv.weight.mul_(2.0)                                             # in-place update -> new version
+    w2 = layers._weight_cl(conv)
+    assert w2 is not w1 and torch.equal(w2, conv.weight)
+    conv.load_state_dict({"weight": torch.ones_like(conv.weight)})
+    assert torch.equal(layers._weight_cl(conv), torch.ones_like(conv.weight))
+    one = torch.nn.Conv2d(8, 16, 1, bias=False)                           # 1x1 filters already satisfy channels_last
+    assert layers._weight_cl(one) is one.weight
+
+
+def test_ctx_map_is_converted_once():
+    """layers._ctx_i32: the frame -> prompt index tensor reaches the C ABI as int32 and is converted once per tensor."""
+    from controlanimate_b200 import layers
+    assert layers._ctx_i32(None) is None
+    m = torch.arange(6) % 3
+    a = layers._ctx_i32(m)
+    assert a.dtype == torch.int32 and a.tolist() == [0, 1, 2, 0, 1, 2]
+    assert layers._ctx_i32(m) is a
