@@ -183,6 +183,8 @@ ATTN_CASES = [
     (2, 5, 7, 8, 8),       # tiny golden-shaped case (f not a multiple of 8)
     (1, 12, 6, 4, 16),
     (1, 1, 3, 2, 8),       # single frame: softmax over one key
+    # the remaining (frames, head_dim) compile-time specialisations: 8/24/32 frames x 40/80/160
+    (1, 8, 10, 8, 80), (1, 8, 12, 8, 160), (1, 24, 9, 8, 40), (1, 24, 6, 8, 160), (1, 32, 7, 8, 80), (1, 32, 5, 8, 160),
 ]
 
 
