@@ -133,10 +133,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
                           const float* __restrict__ pe, long long rows, int c, int f, int d, float eps) {
   constexpr int VEC = 8;
   constexpr int R = 32 / LPR;
+  // gamma | beta | pe[frame of the CTA's first row] | pe[next frame]: staged once per CTA.  r01e's capture showed the first
+  // form of this kernel (parameters by __ldg per row) at 88 % L1TEX throughput: 96 B of fp32 parameters per 16 B of data.
+  extern __shared__ __align__(16) float s_prm[];
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, sl = lane % LPR;
   const int nvec = c / VEC;
-  const long long row = ((long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * R + sub;
+  const long long cta_row0 = (long long)blockIdx.x * kWarpsPerCta * R;
+  const long long row = cta_row0 + (long long)(threadIdx.x >> 5) * R + sub;
   const bool live = row < rows;
   const float inv_c = 1.0f / (float)c;
   uint4 raw[NV];
@@ -145,6 +149,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
   for (int i = 0; i < NV; ++i) {
     const int vi = sl + i * LPR;
     raw[i] = (live && vi < nvec) ? ldg_stream(xr + vi * VEC) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  // rows of one CTA are consecutive tokens: they touch at most two frames when rows-per-CTA <= d (checked on the host)
+  const long long fr0 = cta_row0 / d;
+  const int f0 = (int)(fr0 % f), f1 = f0 + 1 == f ? 0 : f0 + 1;
+  {
+    const int c4 = c / 4;
+    const int parts = pe ? 4 : 2;
+    for (int i = threadIdx.x; i < parts * c4; i += blockDim.x) {
+      const int which = i / c4, j = i - which * c4;
+      const float* src = which == 0 ? gamma : which == 1 ? beta : which == 2 ? pe + (long long)f0 * c : pe + (long long)f1 * c;
+      reinterpret_cast<float4*>(s_prm)[i] = __ldg(reinterpret_cast<const float4*>(src) + j);
+    }
   }
   float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -181,9 +197,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = rsqrtf(sq * inv_c + eps);
+  __syncthreads();  // parameters staged (every thread reaches this: no early exit above)
   if (!live) return;
   const float2 rstd2 = make_float2(rstd, rstd), nmr2 = make_float2(-mean * rstd, -mean * rstd);
-  const float* per = pe ? pe + (long long)((row / d) % f) * c : nullptr;
+  const float* s_g = s_prm;
+  const float* s_b = s_prm + c;
+  const float* per = pe ? s_prm + 2 * c + ((row / d) != fr0 ? c : 0) : nullptr;
   T* yr = y + row * c;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -196,11 +215,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
       unpack2(raw[i].w, v[3].x, v[3].y, T());
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + vi * VEC + 4 * j));
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + vi * VEC + 4 * j));
+        const float4 g4 = *reinterpret_cast<const float4*>(s_g + vi * VEC + 4 * j);
+        const float4 b4 = *reinterpret_cast<const float4*>(s_b + vi * VEC + 4 * j);
         float2 b01 = make_float2(b4.x, b4.y), b23 = make_float2(b4.z, b4.w);
         if (per) {
-          const float4 p4 = __ldg(reinterpret_cast<const float4*>(per + vi * VEC + 4 * j));
+          const float4 p4 = *reinterpret_cast<const float4*>(per + vi * VEC + 4 * j);
           b01 = __fadd2_rn(b01, make_float2(p4.x, p4.y));
           b23 = __fadd2_rn(b23, make_float2(p4.z, p4.w));
         }
@@ -422,7 +441,8 @@ extern "C" __attribute__((visibility("default"))) int ca_layernorm_pe(const void
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static const int ln_mode = [] { const char* e = getenv("CA_LN_MODE"); return !e ? 0 : (e[0] == 'f' ? 1 : (e[0] == 'r' ? 2 : (e[0] == 'p' ? 3 : 0))); }();
   // 0 auto, 1 flat (non-persistent), 2 ring, 3 persistent register-resident
-  if ((ln_mode == 1 || ln_mode == 0) && dtype != CA_F32 && nv <= 5 && aligned16(gamma) && aligned16(beta)) {
+  if ((ln_mode == 1 || ln_mode == 0) && dtype != CA_F32 && nv <= 5 && aligned16(gamma) && aligned16(beta) &&
+      (!pe || kWarpsPerCta * (32 / lpr) <= d)) {  // a CTA's rows touch at most two frames
     const int rc2 = dispatch_dtype(dtype, [&](auto tag) -> int {
       using T = decltype(tag);
       if constexpr (sizeof(T) == 2) {
@@ -430,8 +450,10 @@ extern "C" __attribute__((visibility("default"))) int ca_layernorm_pe(const void
           const int rows_per_cta = kWarpsPerCta * (32 / lpr);
           const long long grid = (rows + rows_per_cta - 1) / rows_per_cta;
           if (grid >= (1ll << 31)) return CA_ERR_UNSUPPORTED;
-          kernel<<<(unsigned)grid, kWarpsPerCta * 32, 0, st>>>(reinterpret_cast<const T*>(x), reinterpret_cast<T*>(y), gamma, beta, pe,
-                                                               rows, c, f, d, eps);
+          const size_t prm = (size_t)(pe ? 4 : 2) * c * sizeof(float);
+          if (prm > 48 * 1024) return CA_ERR_UNSUPPORTED;
+          kernel<<<(unsigned)grid, kWarpsPerCta * 32, prm, st>>>(reinterpret_cast<const T*>(x), reinterpret_cast<T*>(y), gamma, beta, pe,
+                                                                 rows, c, f, d, eps);
           return CA_OK;
         };
 #define CA_LNF_CASE(L_, N_) if (lpr == L_ && nv <= N_) return run(layernorm_flat_kernel<T, L_, N_>)
