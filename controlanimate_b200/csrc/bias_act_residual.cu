@@ -17,9 +17,10 @@ constexpr int kThreads = 256;
 constexpr int kUnroll = 4;
 
 template <typename T, int ACT, bool RES>
-__global__ void __launch_bounds__(kThreads) bias_act_residual_kernel(const T* __restrict__ x, const float* __restrict__ bias,
-                                                                     const T* __restrict__ res, T* __restrict__ y,
+__global__ void __launch_bounds__(kThreads) bias_act_residual_kernel(const T* x, const float* __restrict__ bias, const T* res, T* y,
                                                                      long long nvec, int cvec, float scale) {
+  // x / res / y carry no __restrict__ and are read without .nc: the epilogue runs in place (y == x or y == res); every
+  // thread reads its own vectors before it writes them, which is all the aliasing this kernel allows
   constexpr int VEC = Traits<T>::kVec;
   const long long v0 = (long long)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
   uint4 xv[kUnroll], rv[kUnroll];
@@ -29,8 +30,8 @@ __global__ void __launch_bounds__(kThreads) bias_act_residual_kernel(const T* __
     const long long i = v0 + (long long)u * kThreads;
     ok[u] = i < nvec;
     if (ok[u]) {
-      xv[u] = ldg_stream(x + i * VEC);
-      if constexpr (RES) rv[u] = ldg_stream(res + i * VEC);
+      xv[u] = ldg_stream_rw(x + i * VEC);
+      if constexpr (RES) rv[u] = ldg_stream_rw(res + i * VEC);
     }
   }
 #pragma unroll

@@ -113,6 +113,16 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
                : "l"(p));
   return r;
 }
+// Same streaming load WITHOUT the read-only (.nc) path: for operands the kernel may also write (in-place epilogues,
+// `dst += ...`).  PTX requires .nc data to stay unmodified for the whole kernel, aliasing included.
+__device__ __forceinline__ uint4 ldg_stream_rw(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
 __device__ __forceinline__ uint4 ldg_keep(const void* p) {  // plain (L1/L2-allocating) load
   return *reinterpret_cast<const uint4*>(p);
 }

@@ -1,4 +1,4 @@
-// Dense projections on the 5th-generation tensor cores, CTA-pair edition (tcgen05.mma.cta_group::2).
+// Dense projections on the 5th-generation tensor cores, CTA-pair edition (tcgen05.mma.cta_group::2), round 2.
 //
 //   y[m, n_out] = epilogue( x[m, k] @ w[n, k]^T + bias[n] ) (+ residual[m, n_out])
 //
@@ -7,25 +7,27 @@
 // the spatial transformer (attention.py:133,157-162,268-289), which the reference runs as separate cuBLAS
 // GEMMs + elementwise bias / residual / GEGLU passes.
 //
-// Why a CTA pair (profiles/r01a_gemm_ncu.md): an SM ingests at most ~43 B/clk from L2 (6300 B/clk chip-wide; the
-// 1-CTA kernel sat exactly on that line with 45 % tensor-pipe utilisation).  A 128 x BN tile per SM needs
-// (128 + BN) * 2 B per 256 * BN flop; two SMs sharing one 256 x BN tile each load their 128 rows of A and only
-// HALF of B (the tensor core reads the other half from the peer's shared memory), and when the whole K extent of
-// the B block fits in shared memory it is loaded ONCE per CTA ("B-stationary", K = 320: the 64x64-latent level)
-// so that only A streams: 128 * 2 B per 256 * BN flop.
+// What bounds it (profiles/r01_gemm_notes.md, profiles/r02_gemm_notes.md):
+//   * an SM ingests ~40 B/clk from L2, so operand bytes per flop per SM decide the tensor-pipe ceiling: a CTA PAIR shares
+//     one 256 x BN tile (each SM loads its 128 rows of A and HALF of B), the B block of a pair stays resident in shared
+//     memory whenever its whole K extent fits ("B-stationary": only A streams), and for long K with narrow N the tile
+//     covers up to 512 accumulator columns (two UMMA sub-tiles sharing every A stage, single TMEM stage);
+//   * round 1's epilogue (TMEM -> registers -> swizzled smem slot -> transposed st.global, 46 KB of SASS) took ~2000
+//     cycles per 32 x 32 box; it is now TMEM -> registers -> 32-byte st.global per lane (one full sector each), the
+//     residual arrives by 32-byte ld.global issued before the accumulator is awaited, no shared memory is touched and the
+//     kernel is specialised per epilogue so that each instance stays small;
+//   * exact-erf GELU cost two MUFU ops per output (rcp + ex2: 2048 MUFU cycles per 128 x 128 tile, more than the 2560
+//     cycles the K = 320 MMAs take); Phi(g) is now an odd degree-19 polynomial on the packed fp32x2 FMA pipe.
 //
 // Roles (per CTA; cluster = 2 CTAs = one TPC, rank 0 is the leader):
-//   warp 0   TMA producer : x tile [128 x 64] + this CTA's half of the w tile [BN/2 x 64] (bf16, K-major,
+//   warp 16  TMA producer : x tile [128 x 64] + this CTA's half of each w sub-tile [BN/2 x 64] (bf16, K-major,
 //                           SWIZZLE_128B) into a smem ring; completion bytes of BOTH CTAs are credited to the
 //                           leader's full barrier (cp.async.bulk.tensor ... .cta_group::2)
-//   warp 1   MMA issuer   : leader only; one thread issues tcgen05.mma.cta_group::2.kind::f16 (M=256, N=BN, K=16);
+//   warp 17  MMA issuer   : leader only; one thread issues tcgen05.mma.cta_group::2.kind::f16 (M=256, N=BN, K=16);
 //                           tcgen05.commit ... .multicast::cluster releases the smem stage in both CTAs and publishes
-//                           the accumulator (each CTA's TMEM holds its own 128 rows x BN fp32 columns, 2 stages)
-//   warp 2   TMEM allocator (cta_group::2, 512 columns)
-//   warps 4-11 epilogue   : 4 TMEM lane quarters x 2 column halves.  Per 32x32 box: tcgen05.ld (32 columns) ->
-//                           +bias -> [GEGLU, packed f32x2 math] -> [+residual: TMA-prefetched two boxes ahead into the
-//                           same SWIZZLE_64B staging slot] -> bf16 -> slot -> TMA tensor store.  Overlaps the next
-//                           tile's MMAs through the second TMEM stage.
+//                           the accumulator (each CTA's TMEM holds its own 128 rows x BN fp32 columns)
+//   warp 18  TMEM allocator (cta_group::2, 512 columns)
+//   warps 0-15 epilogue   : 4 TMEM lane quarters x 4 column parts; 16-column chunks dealt round-robin to the parts.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -39,30 +41,37 @@ namespace {
 constexpr int BM = 128;       // rows per CTA (UMMA_M = 256 per pair)
 constexpr int BK = 64;        // one 128-byte swizzle atom of 16-bit elements
 constexpr int UMMA_K = 16;
-constexpr int kAccCols = 256; // TMEM columns per accumulator stage
-constexpr int kEpiParts = 4;  // epilogue warps per TMEM lane quarter (column parts of the tile)
+constexpr int kEpiParts = 2;  // epilogue warps per TMEM lane quarter
 constexpr int kEpiWarps = 4 * kEpiParts;
-constexpr int kMaxSlots = 3;  // staging slots per epilogue warp: 3 with a residual (TMA-prefetched two boxes ahead), else 1
-constexpr int kSlotBytes = 2048;  // one 32 x 32 box of 16-bit elements
-constexpr int kResAhead = 2;  // residual boxes in flight per warp
 constexpr int kThreads = 128 + 32 * kEpiWarps;
-constexpr int kMaxStages = 8;
+// Warp roles.  The SMSP arbiter favours the HIGHEST warp id among eligible warps (B300_MICROARCH.md), and the single
+// MMA-issuing thread must never queue behind sixteen busy epilogue warps (measured: 257 instead of 128 cycles per UMMA
+// with the issuer in warp 1), so the epilogue owns warps 0-15 and the producer / issuer / allocator sit above them.
+constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1, kAllocWarp = kEpiWarps + 2;
+constexpr int kMaxStages = 12;
+constexpr int kMaxSlots = 4;    // staging slots per epilogue warp: 4 with a residual (TMA-prefetched two boxes ahead), else 2
+constexpr int kSlotBytes = 2048;  // one 32 x 32 box of 16-bit elements (SWIZZLE_64B)
 constexpr uint32_t kABytes = BM * BK * 2;
+enum { EPI_BIAS = 0, EPI_RES = 1, EPI_GEGLU = 2 };
 
 struct PairParams {
   long long m;
-  int n, k, bn, n_out;  // bn = accumulator columns per tile; n_out = output columns (n, or n/2 for GEGLU)
-  int geglu, has_res;
+  int n, k;
+  int bn;        // accumulator columns of one UMMA sub-tile (UMMA N)
+  int nsub;      // sub-tiles per tile: they share every A stage (nsub * bn accumulator columns per tile)
+  int out_cols;  // output columns per tile: nsub * bn, or bn / 2 (GEGLU)
   int num_m_blocks, num_n_blocks, num_k_blocks, stages;  // m blocks of 256 rows
-  int stationary;       // the B block of this pair stays in smem for the whole kernel
-  int slots;            // staging slots per epilogue warp
-  long long tiles, tile_step;
+  int stationary;  // the pair keeps the B block of its current n-block in smem; tiles are dealt as contiguous ranges
+  int acc_stages;  // TMEM accumulator stages: 2 when nsub * bn <= 256, else 1
+  long long tiles;
   const float* bias;
   void* y;
-  long long ldy;
-  int dbg;            // development aid (CA_GEMM_DBG): 1 = epilogue only releases TMEM, 2 = tcgen05.ld but no stores
+  const void* res;
+  long long ldy, ldr;
+  int slots;          // staging slots per epilogue warp
+  int roles_low;      // development aid (CA_GEMM_ROLES_LOW=1): producer / issuer / allocator in warps 0-2 instead of 16-18
   long long* timing;  // CA_GEMM_TIMING=1: per-CTA cycle counters [gridDim.x][8] (development aid), else null
-  uint32_t idesc, b_bytes, b_stride, stage_bytes, bres_bytes;  // b_bytes: this CTA's half tile; b_stride: 1024-aligned
+  uint32_t idesc, b_bytes, b_stride, stage_bytes, bres_bytes;  // b_*: this CTA's half of ONE sub-tile k-block
 };
 
 // ---- tcgen05 wrappers (cta_group::2) --------------------------------------------------------
@@ -92,6 +101,14 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, u
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
@@ -100,14 +117,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }
@@ -152,37 +161,35 @@ __device__ __forceinline__ f2 add2(f2 a, f2 b) {
   return d;
 }
 __device__ __forceinline__ f2 splat(float c) { return pk(c, c); }
-
-__device__ __forceinline__ float rcp_approx(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+  float d;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
 }
 
-// a * GELU(g) for two columns, exact-erf definition (diffusers GEGLU uses F.gelu default).  erfc by Abramowitz-Stegun
-// 7.1.26 (abs err <= 1.5e-7): Phi(g) = 1/2 + copysign(1/2 - erfc(|g|/sqrt2)/2, g).  With z' = |g| * sqrt(log2(e)/2) the
-// Gaussian factor is ex2(-z'^2); the polynomial runs on packed fp32x2 (11.5 issue slots per output instead of ~32).
+// a * GELU(g) for two columns, exact-erf definition (diffusers GEGLU uses F.gelu default): GELU(g) = g * Phi(g),
+// Phi(g) = 1/2 + erf(g / sqrt 2) / 2.  With s = g / 4.5 and u = min(s^2, 1):  Phi(g) = sat(1/2 + s * P(u)), P of degree 9
+// fitted on |g| <= 4.5 (max |error of Phi| 9e-6 including the clamp: 1 - Phi(4.5) = 3.4e-6; beyond the fit interval
+// s * P(1) keeps growing in magnitude and the saturation returns exactly 0 or 1).  No MUFU: ten packed FMAs per PAIR of
+// outputs instead of rcp + ex2 per output.
 __device__ __forceinline__ f2 geglu2(f2 a, f2 g) {
-  float g0, g1;
-  upk(g, g0, g1);
-  const f2 zp = mul2(pk(fabsf(g0), fabsf(g1)), splat(0.84932180028801904f));        // |g| * sqrt(log2e / 2)
-  const f2 d = fma2(zp, splat(0.3275911f * 0.83255461115769776f), splat(1.0f));     // 1 + p |g| / sqrt2
-  float d0, d1;
-  upk(d, d0, d1);
-  const f2 t = pk(rcp_approx(d0), rcp_approx(d1));
-  f2 poly = fma2(t, splat(-0.5f * 1.061405429f), splat(-0.5f * -1.453152027f));     // coefficients pre-halved, negated
-  poly = fma2(poly, t, splat(-0.5f * 1.421413741f));
-  poly = fma2(poly, t, splat(-0.5f * -0.284496736f));
-  poly = fma2(poly, t, splat(-0.5f * 0.254829592f));
-  poly = mul2(poly, t);
-  const f2 w = mul2(zp, zp);
-  float w0, w1;
-  upk(w, w0, w1);
-  const f2 e = pk(exp2f(-w0), exp2f(-w1));                                          // --use_fast_math: MUFU.EX2
-  const f2 half_erf = fma2(poly, e, splat(0.5f));                                   // 1/2 - erfc/2  (>= 0)
-  float h0, h1;
-  upk(half_erf, h0, h1);
-  const f2 phi = add2(pk(copysignf(h0, g0), copysignf(h1, g1)), splat(0.5f));
+  const f2 s = mul2(g, splat(1.0f / 4.5f));
+  float s0, s1;
+  upk(mul2(s, s), s0, s1);
+  const f2 u = pk(fminf(s0, 1.0f), fminf(s1, 1.0f));
+  f2 p = fma2(splat(-4.261638838e+00f), u, splat(2.484848156e+01f));
+  p = fma2(p, u, splat(-6.462894735e+01f));
+  p = fma2(p, u, splat(9.980938078e+01f));
+  p = fma2(p, u, splat(-1.031514738e+02f));
+  p = fma2(p, u, splat(7.648830514e+01f));
+  p = fma2(p, u, splat(-4.258644516e+01f));
+  p = fma2(p, u, splat(1.823896685e+01f));
+  p = fma2(p, u, splat(-6.051783177e+00f));
+  p = fma2(p, u, splat(1.795147712e+00f));
+  float p0, p1;
+  upk(p, p0, p1);
+  upk(s, s0, s1);
+  const f2 phi = pk(fma_sat(s0, p0, 0.5f), fma_sat(s1, p1, 0.5f));
   return mul2(mul2(a, g), phi);
 }
 
@@ -201,35 +208,76 @@ __device__ __forceinline__ f2 unpack_f2(uint32_t w) {
 
 // mbarrier wait that adds the cycles spent to `acc` when timing is on
 __device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, bool on, long long& acc) {
-  if (!on) {
-    mbar_wait(bar, parity);
-    return;
-  }
-  const long long t0 = clock64();
+  const long long t0 = on ? clock64() : 0;
   mbar_wait(bar, parity);
-  acc += clock64() - t0;
+  if (on) acc += clock64() - t0;
 }
 
-template <typename T>
+// The tiles of one pair, in the order all three roles walk them (32-bit, division-free stepping).
+//   stationary: tiles are numbered n-block-major (t = nb * num_m_blocks + mb) and pair p owns the contiguous range
+//               [p * tiles / pairs, (p + 1) * tiles / pairs): balanced to within one tile, and the n-block (hence the
+//               resident B block) changes at most a few times per pair
+//   otherwise : round robin, n-block-minor (t = mb * num_n_blocks + nb): concurrently running pairs share A and B in L2
+struct TileWalk {
+  int left, mb_, nb_, step_mb, step_nb, num_m_blocks, num_n_blocks, stationary;
+  __device__ TileWalk(const PairParams& p, int pair, int pairs)
+      : num_m_blocks(p.num_m_blocks), num_n_blocks(p.num_n_blocks), stationary(p.stationary) {
+    const int tiles = (int)p.tiles;
+    if (stationary) {
+      const int t0 = (int)((long long)pair * tiles / pairs), t1 = (int)((long long)(pair + 1) * tiles / pairs);
+      left = t1 - t0;
+      nb_ = t0 / num_m_blocks;
+      mb_ = t0 - nb_ * num_m_blocks;
+      step_mb = step_nb = 0;
+    } else {
+      left = pair < tiles ? (tiles - pair + pairs - 1) / pairs : 0;
+      mb_ = pair / num_n_blocks;
+      nb_ = pair - mb_ * num_n_blocks;
+      step_mb = pairs / num_n_blocks;
+      step_nb = pairs - step_mb * num_n_blocks;
+    }
+  }
+  __device__ bool valid() const { return left > 0; }
+  __device__ void next() {
+    --left;
+    if (stationary) {
+      if (++mb_ == num_m_blocks) {
+        mb_ = 0;
+        ++nb_;
+      }
+    } else {
+      mb_ += step_mb;
+      nb_ += step_nb;
+      if (nb_ >= num_n_blocks) {
+        nb_ -= num_n_blocks;
+        ++mb_;
+      }
+    }
+  }
+  __device__ int nb() const { return nb_; }
+  __device__ int mb() const { return mb_; }
+};
+
+template <typename T, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                     const __grid_constant__ CUtensorMap map_r,
-                     const PairParams p) {
+                     const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_r, const PairParams p) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
-  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tmem_full[2], tmem_empty[2], bres_full;
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tmem_full[2], tmem_empty[2], bres_full, bres_empty;
   __shared__ uint64_t res_full[kEpiWarps][kMaxSlots];
   __shared__ uint32_t tmem_base_slot;
 
   // SWIZZLE_128B tiles must start on 1024-byte boundaries (same offsets in both CTAs of the pair)
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  unsigned char* bres = smem;                        // [num_k_blocks][b_stride] when stationary
-  unsigned char* ring = smem + p.bres_bytes;         // [stages][stage_bytes]: A tile (+ B half tile)
+  unsigned char* bres = smem;                 // [num_k_blocks][nsub][b_stride] when stationary
+  unsigned char* ring = smem + p.bres_bytes;  // [stages][stage_bytes]: A tile (+ nsub B half tiles)
   unsigned char* slots = ring + (size_t)p.stages * p.stage_bytes;  // [kEpiWarps][p.slots][kSlotBytes]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_phys = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = p.roles_low ? (warp_phys < 4 ? warp_phys + kEpiWarps : warp_phys - 4) : warp_phys;  // role index
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const long long pair = blockIdx.x >> 1;
+  const int pair = blockIdx.x >> 1, pairs = gridDim.x >> 1;
   const int stages = p.stages;
 
   if (threadIdx.x == 0) {
@@ -239,14 +287,15 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-        mbar_init(&tmem_empty[s], 2 * kEpiWarps);  // epilogue warps of both CTAs
+      mbar_init(&tmem_empty[s], 2 * kEpiWarps);  // epilogue warps of both CTAs
     }
     mbar_init(&bres_full, 1);
+    mbar_init(&bres_empty, 1);
     for (int w = 0; w < kEpiWarps; ++w)
-      for (int s = 0; s < kMaxSlots; ++s) mbar_init(&res_full[w][s], 1);
+      for (int sl = 0; sl < kMaxSlots; ++sl) mbar_init(&res_full[w][sl], 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc_pair(&tmem_base_slot, 512);
+  if (warp == kAllocWarp) tmem_alloc_pair(&tmem_base_slot, 512);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // barrier inits of the peer are visible before any remote arrive / multicast commit
@@ -255,87 +304,107 @@ __global__ void __launch_bounds__(kThreads, 1)
   const bool timing = p.timing != nullptr;
   long long t_wait_a = 0, t_wait_b = 0;
   const long long t_begin = timing ? clock64() : 0;
-  const bool active = !(p.stationary && pair >= p.tile_step);  // stationary: pairs beyond G * n_blocks have no tiles
   const int half = p.bn / 2;
 
-  if (warp == 0) {
-    // ===================== TMA producer (one thread per CTA) =====================
-    if (active) {  // the whole warp walks the loop (convergent, warp-uniform state); one elected lane issues
-      if (lane == 0) {
-        prefetch_tensormap(&map_x);
-        prefetch_tensormap(&map_w);
-      }
-      // rows of w this CTA supplies for n-block nb: plain = its half of [n0, n0+BN); GEGLU = values (rank 0) / gates (rank 1)
-      auto b_row = [&](int nb) { return p.geglu ? (int)rank * (p.n / 2) + nb * half : nb * p.bn + (int)rank * half; };
-      if (p.stationary) {
-        const int nb = (int)(pair % p.num_n_blocks);
-        const uint32_t bar = mapa_u32(&bres_full, 0);
+  if (warp == kProducerWarp) {
+    // ===================== TMA producer (the whole warp walks the loop; one elected lane issues) =====================
+    if (lane == 0) {
+      prefetch_tensormap(&map_x);
+      prefetch_tensormap(&map_w);
+    }
+    // rows of w this CTA supplies for sub-tile j of n-block nb: its half of the sub-tile's columns, or (GEGLU) the value
+    // rows (rank 0) / gate rows (rank 1) of the n-block
+    auto b_row = [&](int nb, int j) {
+      return EPI == EPI_GEGLU ? (int)rank * (p.n / 2) + nb * half : (nb * p.nsub + j) * p.bn + (int)rank * half;
+    };
+    const uint32_t bres_bar = mapa_u32(&bres_full, 0);
+    const uint32_t stage_tx = kABytes + (p.stationary ? 0u : (uint32_t)p.nsub * p.b_bytes);
+    int stage = 0, cur_nb = -1;
+    uint32_t phase = 0, loads = 0;
+    for (TileWalk w(p, pair, pairs); w.valid(); w.next()) {
+      const int nb = w.nb();
+      if (p.stationary && nb != cur_nb) {
+        // (re)load the resident B block; the previous block must have been consumed by the MMAs first
+        if (loads) timed_wait(&bres_empty, (loads - 1) & 1, timing, t_wait_b);
         if (elect_one()) {
-          if (leader) mbar_arrive_expect_tx(&bres_full, 2u * p.b_bytes * (uint32_t)p.num_k_blocks);
+          if (leader) mbar_arrive_expect_tx(&bres_full, 2u * p.b_bytes * (uint32_t)(p.num_k_blocks * p.nsub));
           for (int kb = 0; kb < p.num_k_blocks; ++kb)
-            tma_load_2d_pair(bres + (size_t)kb * p.b_stride, &map_w, bar, kb * BK, b_row(nb));
+            for (int j = 0; j < p.nsub; ++j)
+              tma_load_2d_pair(bres + (size_t)(kb * p.nsub + j) * p.b_stride, &map_w, bres_bar, kb * BK, b_row(nb, j));
         }
         __syncwarp();
+        cur_nb = nb;
+        ++loads;
       }
-      const uint32_t stage_tx = kABytes + (p.stationary ? 0u : p.b_bytes);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long tile = pair; tile < p.tiles; tile += p.tile_step) {
-        const int nb = (int)(tile % p.num_n_blocks);
-        const int mb = (int)(tile / p.num_n_blocks);
-        const int a_row = mb * 2 * BM + (int)rank * BM;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          timed_wait(&empty_bar[stage], phase ^ 1, timing, t_wait_a);
-          unsigned char* sa = ring + (size_t)stage * p.stage_bytes;
-          const uint32_t bar = mapa_u32(&full_bar[stage], 0);
-          // Only the leader arrives (expecting the bytes of both CTAs); the peer just issues its loads.  A peer load
-          // of phase n+1 cannot land before the leader's barrier finished phase n: the peer waits on empty_bar, which
-          // the leader's MMAs signal only after consuming phase n.  (A remote release-arrive here costs a MEMBAR per
-          // k-block on the producer's critical path: 3x slower main loop, profiles/r01b.)
-          if (elect_one()) {
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * stage_tx);
-            tma_load_2d_pair(sa, &map_x, bar, kb * BK, a_row);
-            if (!p.stationary) tma_load_2d_pair(sa + kABytes, &map_w, bar, kb * BK, b_row(nb));
-          }
-          __syncwarp();
-          if (++stage == stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+      const int a_row = w.mb() * 2 * BM + (int)rank * BM;
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        timed_wait(&empty_bar[stage], phase ^ 1, timing, t_wait_a);
+        unsigned char* sa = ring + (size_t)stage * p.stage_bytes;
+        const uint32_t bar = mapa_u32(&full_bar[stage], 0);
+        // Only the leader arrives (expecting the bytes of both CTAs); the peer just issues its loads.  A peer load
+        // of phase n+1 cannot land before the leader's barrier finished phase n: the peer waits on empty_bar, which
+        // the leader's MMAs signal only after consuming phase n.  (A remote release-arrive here costs a MEMBAR per
+        // k-block on the producer's critical path: 3x slower main loop, profiles/r01b.)
+        if (elect_one()) {
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * stage_tx);
+          tma_load_2d_pair(sa, &map_x, bar, kb * BK, a_row);
+          if (!p.stationary)
+            for (int j = 0; j < p.nsub; ++j)
+              tma_load_2d_pair(sa + kABytes + (size_t)j * p.b_stride, &map_w, bar, kb * BK, b_row(nb, j));
+        }
+        __syncwarp();
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
-      if (timing && lane == 0) p.timing[blockIdx.x * 8 + 3] = t_wait_a;
     }
-  } else if (warp == 1) {
+    if (timing && lane == 0) {
+      p.timing[blockIdx.x * 8 + 3] = t_wait_a;
+      p.timing[blockIdx.x * 8 + 4] = t_wait_b;
+    }
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (one thread of the leader CTA) =====================
-    if (leader && active) {  // convergent warp; tcgen05.mma / commit by one elected lane
-      if (p.stationary) {
-        mbar_wait(&bres_full, 0);
+    if (leader) {  // convergent warp; tcgen05.mma / commit by one elected lane
+      int stage = 0, cur_nb = -1;
+      uint32_t phase = 0, loads = 0;
+      long long it = 0, t_wait_c = 0;
+      TileWalk w(p, pair, pairs);
+      while (w.valid()) {
+        const int nb = w.nb();
+        if (p.stationary && nb != cur_nb) {
+          timed_wait(&bres_full, loads & 1, timing, t_wait_c);
+          tc_fence_after();
+          cur_nb = nb;
+          ++loads;
+        }
+        const int acc = p.acc_stages == 2 ? (int)(it & 1) : 0;
+        const uint32_t acc_par = p.acc_stages == 2 ? (uint32_t)((it >> 1) & 1) : (uint32_t)(it & 1);
+        timed_wait(&tmem_empty[acc], acc_par ^ 1, timing, t_wait_a);
         tc_fence_after();
-      }
-      int stage = 0;
-      uint32_t phase = 0;
-      long long it = 0;
-      for (long long tile = pair; tile < p.tiles; tile += p.tile_step, ++it) {
-        const int acc = (int)(it & 1);
-        timed_wait(&tmem_empty[acc], (uint32_t)((it >> 1) & 1) ^ 1, timing, t_wait_a);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)acc * kAccCols;
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
+        w.next();
+        const bool last_of_block = p.stationary && (!w.valid() || w.nb() != nb);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           timed_wait(&full_bar[stage], phase, timing, t_wait_b);
           tc_fence_after();
           const uint32_t sa = smem_u32(ring + (size_t)stage * p.stage_bytes);
-          const uint32_t sb = p.stationary ? smem_u32(bres + (size_t)kb * p.b_stride) : sa + kABytes;
-          const uint64_t adesc = make_sw128_desc(sa);
-          const uint64_t bdesc = make_sw128_desc(sb);
+          const uint32_t sb = p.stationary ? smem_u32(bres + (size_t)(kb * p.nsub) * p.b_stride) : sa + kABytes;
+          const uint64_t adesc = make_sw128_desc(sa), bdesc0 = make_sw128_desc(sb), bdesc1 = make_sw128_desc(sb + p.b_stride);
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < BK / UMMA_K; ++ks) {
               // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
-              umma_f16_pair(tmem_d, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), p.idesc, (kb | ks) != 0 ? 1u : 0u);
+              umma_f16_pair(tmem_d, adesc + (uint64_t)(ks * 2), bdesc0 + (uint64_t)(ks * 2), p.idesc, (kb | ks) != 0 ? 1u : 0u);
+              if (p.nsub == 2)
+                umma_f16_pair(tmem_d + (uint32_t)p.bn, adesc + (uint64_t)(ks * 2), bdesc1 + (uint64_t)(ks * 2), p.idesc,
+                              (kb | ks) != 0 ? 1u : 0u);
             }
             umma_commit_pair(&empty_bar[stage]);  // frees this smem stage in both CTAs once the MMAs above have read it
-            if (kb == p.num_k_blocks - 1) umma_commit_pair(&tmem_full[acc]);
+            if (kb == p.num_k_blocks - 1) {
+              umma_commit_pair(&tmem_full[acc]);
+              if (last_of_block) umma_commit_pair(&bres_empty);
+            }
           }
           __syncwarp();
           if (++stage == stages) {
@@ -343,28 +412,30 @@ __global__ void __launch_bounds__(kThreads, 1)
             phase ^= 1;
           }
         }
+        ++it;
       }
       if (timing && lane == 0) {
         p.timing[blockIdx.x * 8 + 0] = clock64() - t_begin;
         p.timing[blockIdx.x * 8 + 1] = t_wait_a;
         p.timing[blockIdx.x * 8 + 2] = t_wait_b;
+        p.timing[blockIdx.x * 8 + 5] = t_wait_c;
       }
     }
-  } else if (warp >= 4 && active) {
-    // ===================== epilogue: TMEM -> registers -> swizzled smem slot -> TMA store =====================
-    // warp w drains TMEM lane quarter q = w % 4 (hardware restriction) and column part (w - 4) / 4 of the tile, one
-    // 32 x 32 box at a time (two tcgen05.ld of 16 columns).  Each warp owns `nslots` 2 KB staging slots
-    // (SWIZZLE_64B: conflict-free 16-byte accesses); with a residual the slot is first filled by a TMA load issued two
-    // boxes earlier, the sum is written back in place and the slot leaves through a TMA tensor store.
-    const int ew = warp - 4, q = warp & 3, part = ew >> 2;
-    const int out_cols = p.geglu ? half : p.bn;
-    const int boxes = out_cols / 32;
-    const int b_begin = (boxes * part) / kEpiParts, b_end = (boxes * (part + 1)) / kEpiParts;
+  } else if (warp < kEpiWarps) {
+    // ===================== epilogue: TMEM -> registers -> swizzled smem box -> TMA store =====================
+    // warp w drains TMEM lane quarter q = w % 4 (hardware restriction); the tile's 32-column boxes are dealt round robin to
+    // the parts.  A lane owns one output row, so a direct st.global would touch 32 different cache lines per instruction
+    // (measured: ~66 L1TEX cycles per store instruction, 4400 cycles per 128 x 256 tile — longer than the K = 320 MMAs);
+    // instead the box is written to a SWIZZLE_64B slot (conflict-free 16-byte st.shared) and leaves through the TMA
+    // engine, and the residual box arrives the same way (TMA load issued two boxes ahead into the slot ring).
+    const int q = warp & 3, part = warp >> 2;
+    const int n_boxes = p.out_cols >> 5;
+    const int my_n = (n_boxes - part + kEpiParts - 1) / kEpiParts;  // boxes part, part + kEpiParts, ...
     const uint32_t nslots = (uint32_t)p.slots;
-    unsigned char* my_slots = slots + (size_t)ew * nslots * kSlotBytes;
-    const int sw = (lane >> 1) & 3;  // SWIZZLE_64B: 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)
+    unsigned char* my_slots = slots + (size_t)warp * nslots * kSlotBytes;
+    const int sw = (lane >> 1) & 3;  // SWIZZLE_64B: 16-byte unit u of row r sits at unit u ^ ((r >> 1) & 3)
     const uint32_t empty_remote0 = mapa_u32(&tmem_empty[0], 0), empty_remote1 = mapa_u32(&tmem_empty[1], 0);
-    auto release_acc = [&](int acc) {  // TMEM stage fully read by this warp (tcgen05.wait::ld done): hand it back
+    auto release_acc = [&](int acc) {  // this warp's share of the stage is in registers (tcgen05.wait::ld done)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -372,62 +443,68 @@ __global__ void __launch_bounds__(kThreads, 1)
         else mbar_arrive_cluster_relaxed(acc ? empty_remote1 : empty_remote0);
       }
     };
-    if (lane == 0 && p.has_res) prefetch_tensormap(&map_r);
-    T* __restrict__ y = reinterpret_cast<T*>(p.y);
-    auto tile_row0 = [&](long long tile) { return (int)(tile / p.num_n_blocks) * 2 * BM + (int)rank * BM + q * 32; };
-    auto tile_col0 = [&](long long tile) { return (int)(tile % p.num_n_blocks) * out_cols; };
-
-    // residual prefetch cursor (lane 0 only): runs kResAhead boxes ahead of the compute cursor
-    long long pf_tile = pair;
-    int pf_bx = b_begin;
+    if (lane == 0) {
+      prefetch_tensormap(&map_y);
+      if (EPI == EPI_RES) prefetch_tensormap(&map_r);
+    }
+    // residual prefetch cursor (meaningful in lane 0 only): runs two boxes ahead of the compute cursor
+    TileWalk pf(p, pair, pairs);
+    int pf_i = 0;
     uint32_t pf_slot = 0;
     auto prefetch_one = [&]() {
-      if (pf_tile >= p.tiles) return;
-      mbar_arrive_expect_tx(&res_full[ew][pf_slot], kSlotBytes);
-      tma_load_2d(my_slots + pf_slot * kSlotBytes, &map_r, &res_full[ew][pf_slot], tile_col0(pf_tile) + pf_bx * 32,
-                  tile_row0(pf_tile));
+      if (!pf.valid() || my_n == 0) return;
+      mbar_arrive_expect_tx(&res_full[warp][pf_slot], kSlotBytes);
+      tma_load_2d(my_slots + pf_slot * kSlotBytes, &map_r, &res_full[warp][pf_slot],
+                  pf.nb() * p.out_cols + (part + pf_i * kEpiParts) * 32, pf.mb() * 2 * BM + (int)rank * BM + q * 32);
       if (++pf_slot == nslots) pf_slot = 0;
-      if (++pf_bx == b_end) {
-        pf_bx = b_begin;
-        pf_tile += p.tile_step;
+      if (++pf_i == my_n) {
+        pf_i = 0;
+        pf.next();
       }
     };
-    if (b_begin < b_end && p.has_res && lane == 0) {
-#pragma unroll 1
-      for (int i = 0; i < kResAhead; ++i) prefetch_one();
+    if (EPI == EPI_RES && lane == 0) {
+      prefetch_one();
+      prefetch_one();
     }
-
-    uint32_t slot = 0, slot_phase = 0;  // staging slot of the current box; parity of its residual barrier
+    uint32_t slot = 0, slot_phase = 0;
     long long it = 0;
-    for (long long tile = pair; tile < p.tiles; tile += p.tile_step, ++it) {
-      const int acc = (int)(it & 1);
-      const int row0 = tile_row0(tile), n0 = tile_col0(tile);
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kAccCols;
-      timed_wait(&tmem_full[acc], (uint32_t)((it >> 1) & 1), timing, t_wait_a);
+    for (TileWalk w(p, pair, pairs); w.valid(); w.next(), ++it) {
+      const int acc = p.acc_stages == 2 ? (int)(it & 1) : 0;
+      const uint32_t acc_par = p.acc_stages == 2 ? (uint32_t)((it >> 1) & 1) : (uint32_t)(it & 1);
+      const int row0 = w.mb() * 2 * BM + (int)rank * BM + q * 32;
+      const int col0 = w.nb() * p.out_cols;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
+      timed_wait(&tmem_full[acc], acc_par, timing, t_wait_a);
       tc_fence_after();
-      if (b_begin == b_end || p.dbg == 1) {  // nothing to drain for this warp (tile narrower than 128 columns)
-        release_acc(acc);
-        continue;
-      }
+      if (my_n == 0) release_acc(acc);
+      // one box per iteration, NOT unrolled: the hot loops have to stay inside the instruction cache (round 1's fully
+      // unrolled epilogue was 46 KB of SASS)
 #pragma unroll 1
-      for (int bx = b_begin; bx < b_end; ++bx) {
-        const int col = bx * 32;
+      for (int i = 0; i < my_n; ++i) {
+        const int bc = (part + i * kEpiParts) * 32;  // first column of the box inside the tile
         unsigned char* buf = my_slots + slot * kSlotBytes;
-        // the slot refilled below (residual of box + kResAhead) was drained kSlots - kResAhead boxes ago by this warp's
-        // own ld.shared / st.global (program order), so lane 0 may hand it to the TMA engine right away
-        if (p.has_res && lane == 0) prefetch_one();
-        bool res_ready = false;
+        // slot hygiene (bulk groups are per thread: lane 0 issues every TMA store of this warp).  With a residual the
+        // slot refilled now (box + 2) was last read by the store issued two boxes ago; without, the slot written below was
+        // last read by the store issued nslots boxes ago.
+        if (lane == 0) {
+          if (EPI == EPI_RES) {
+            bulk_wait_read<1>();
+            prefetch_one();
+          } else {
+            bulk_wait_read<1>();
+          }
+        }
+        __syncwarp();
+        f2 v[16];
+        if constexpr (EPI == EPI_GEGLU) {
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t r[16];
-          f2 v[8];
-          const int c16 = col + 16 * hh;
-          const int gc = n0 + c16;  // global output column
-          tmem_ld16(taddr + c16, r);
-          if (p.geglu) {
-            uint32_t gt[16];
-            tmem_ld16(taddr + out_cols + c16, gt);
+          for (int h2 = 0; h2 < 2; ++h2) {
+            uint32_t a[16], g[16];
+            tmem_ld16(taddr + (uint32_t)(bc + 16 * h2), a);
+            tmem_ld16(taddr + (uint32_t)(half + bc + 16 * h2), g);
             tmem_ld_wait();
+            if (h2 == 1 && i == my_n - 1) release_acc(acc);
+            const int gc = col0 + bc + 16 * h2;
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
               float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
@@ -435,87 +512,70 @@ __global__ void __launch_bounds__(kThreads, 1)
                 ba = __ldg(reinterpret_cast<const float4*>(p.bias + gc + j));
                 bg = __ldg(reinterpret_cast<const float4*>(p.bias + p.n / 2 + gc + j));
               }
-              const f2 a0 = add2(pk(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), pk(ba.x, ba.y));
-              const f2 a1 = add2(pk(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), pk(ba.z, ba.w));
-              const f2 g0 = add2(pk(__uint_as_float(gt[j]), __uint_as_float(gt[j + 1])), pk(bg.x, bg.y));
-              const f2 g1 = add2(pk(__uint_as_float(gt[j + 2]), __uint_as_float(gt[j + 3])), pk(bg.z, bg.w));
-              v[j / 2] = geglu2(a0, g0);
-              v[j / 2 + 1] = geglu2(a1, g1);
-            }
-          } else {
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 ba = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias) ba = __ldg(reinterpret_cast<const float4*>(p.bias + gc + j));
-              v[j / 2] = add2(pk(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), pk(ba.x, ba.y));
-              v[j / 2 + 1] = add2(pk(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), pk(ba.z, ba.w));
+              v[8 * h2 + j / 2] = geglu2(add2(pk(__uint_as_float(a[j]), __uint_as_float(a[j + 1])), pk(ba.x, ba.y)),
+                                         add2(pk(__uint_as_float(g[j]), __uint_as_float(g[j + 1])), pk(bg.x, bg.y)));
+              v[8 * h2 + j / 2 + 1] = geglu2(add2(pk(__uint_as_float(a[j + 2]), __uint_as_float(a[j + 3])), pk(ba.z, ba.w)),
+                                             add2(pk(__uint_as_float(g[j + 2]), __uint_as_float(g[j + 3])), pk(bg.z, bg.w)));
             }
           }
-          if (hh == 1 && bx == b_end - 1) release_acc(acc);
-          if (p.dbg == 2) {
-            if (__uint_as_float(r[0]) == 123.456f) y[0] = T(v[0].v != 0);
-            continue;
-          }
-          if (p.has_res) {
-            if (!res_ready) {
-              timed_wait(&res_full[ew][slot], slot_phase, timing, t_wait_b);
-              res_ready = true;
-            }
+        } else {
+          uint32_t a[32];
+          tmem_ld32(taddr + (uint32_t)bc, a);
+          tmem_ld_wait();
+          if (i == my_n - 1) release_acc(acc);
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              const uint4 rr = *reinterpret_cast<const uint4*>(buf + lane * 64 + (((2 * hh + c) ^ sw) * 16));
-              v[4 * c + 0] = add2(v[4 * c + 0], unpack_f2<T>(rr.x));
-              v[4 * c + 1] = add2(v[4 * c + 1], unpack_f2<T>(rr.y));
-              v[4 * c + 2] = add2(v[4 * c + 2], unpack_f2<T>(rr.z));
-              v[4 * c + 3] = add2(v[4 * c + 3], unpack_f2<T>(rr.w));
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint4 o;
-            o.x = cvt_pack<T>(v[4 * c + 0]);
-            o.y = cvt_pack<T>(v[4 * c + 1]);
-            o.z = cvt_pack<T>(v[4 * c + 2]);
-            o.w = cvt_pack<T>(v[4 * c + 3]);
-            *reinterpret_cast<uint4*>(buf + lane * 64 + (((2 * hh + c) ^ sw) * 16)) = o;
+          for (int j = 0; j < 32; j += 4) {
+            float4 ba = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) ba = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + bc + j));
+            v[j / 2] = add2(pk(__uint_as_float(a[j]), __uint_as_float(a[j + 1])), pk(ba.x, ba.y));
+            v[j / 2 + 1] = add2(pk(__uint_as_float(a[j + 2]), __uint_as_float(a[j + 3])), pk(ba.z, ba.w));
           }
         }
-        // transposed write-out: the box sits in the slot row-major (64 B rows); every st.global.v4 of the warp now covers
-        // 8 rows x 64 contiguous bytes (full 32-byte sectors) instead of 32 rows x 16 bytes
+        if constexpr (EPI == EPI_RES) {
+          timed_wait(&res_full[warp][slot], slot_phase, timing, t_wait_b);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint4 rr = *reinterpret_cast<const uint4*>(buf + lane * 64 + ((u ^ sw) * 16));
+            v[4 * u + 0] = add2(v[4 * u + 0], unpack_f2<T>(rr.x));
+            v[4 * u + 1] = add2(v[4 * u + 1], unpack_f2<T>(rr.y));
+            v[4 * u + 2] = add2(v[4 * u + 2], unpack_f2<T>(rr.z));
+            v[4 * u + 3] = add2(v[4 * u + 3], unpack_f2<T>(rr.w));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 o;
+          o.x = cvt_pack<T>(v[4 * u + 0]);
+          o.y = cvt_pack<T>(v[4 * u + 1]);
+          o.z = cvt_pack<T>(v[4 * u + 2]);
+          o.w = cvt_pack<T>(v[4 * u + 3]);
+          *reinterpret_cast<uint4*>(buf + lane * 64 + ((u ^ sw) * 16)) = o;
+        }
+        fence_proxy_async();  // generic-proxy writes of the box -> visible to the TMA engine
         __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = i * 8 + (lane >> 2), cc = lane & 3;
-          const uint4 o = *reinterpret_cast<const uint4*>(buf + rr * 64 + ((cc ^ ((rr >> 1) & 3)) * 16));
-          const long long grow = (long long)row0 + rr;
-          if (grow < p.m) stg_stream(y + grow * p.ldy + n0 + col + cc * 8, o);
+        if (lane == 0) {
+          tma_store_2d(&map_y, buf, col0 + bc, row0);  // rows >= m are clipped by the tensor map
+          bulk_commit();
         }
-        __syncwarp();  // all lanes have read the slot before it is refilled / rewritten
         if (++slot == nslots) {
           slot = 0;
           slot_phase ^= 1;
         }
       }
     }
-    if (timing && lane == 0 && q == 0 && part < 2) {  // part 0 and part 1 may own different numbers of boxes
-      p.timing[blockIdx.x * 8 + 4 + 2 * part] = t_wait_a;
-      p.timing[blockIdx.x * 8 + 5 + 2 * part] = t_wait_b;
+    if (lane == 0) bulk_wait<0>();  // the slots must outlive the last stores' reads (and the writes must land before exit)
+    if (timing && lane == 0 && q == 0 && part == 0) {
+      p.timing[blockIdx.x * 8 + 6] = t_wait_a;
+      p.timing[blockIdx.x * 8 + 7] = t_wait_b;
     }
   }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // the peer may still multicast-commit into / read from this CTA's shared memory until here
-  if (warp == 2) {
+  if (warp == kAllocWarp) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, 512);
   }
-}
-
-int pick_bn(int n_cols, int cap) {  // largest multiple of 32 <= cap dividing n_cols (epilogue boxes are 32 columns wide)
-  for (int bn = cap / 32 * 32; bn >= 32; bn -= 32)
-    if (n_cols % bn == 0) return bn;
-  return 0;
 }
 
 int gemm_impl() {  // CA_GEMM_IMPL=1cta selects the single-CTA yardstick kernel
@@ -526,13 +586,61 @@ int gemm_impl() {  // CA_GEMM_IMPL=1cta selects the single-CTA yardstick kernel
   }
   return impl;
 }
-int gemm_stationary_allowed() {  // CA_GEMM_STATIONARY=0 disables the B-stationary schedule (A/B measurements)
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("CA_GEMM_STATIONARY");
-    on = (e && e[0] == '0') ? 0 : 1;
+
+// One way to tile the problem, and what the pair's main loop is expected to cost with it.
+struct Plan {
+  int bn = 0, nsub = 1, stationary = 0, stages = 0, acc_stages = 2;
+  int num_n_blocks = 0;
+  size_t bres_bytes = 0, stage_bytes = 0;
+  double cost = 1e300;
+};
+
+constexpr size_t kSmemBudget = 227 * 1024 - 1024 /*alignment*/ - 1024 /*static*/;
+
+// Cycles per pair under the three per-SM limits this kernel was measured against (profiles/r02_gemm_notes.md): the tensor
+// pipe (BN / 2 cycles per UMMA), the ~40 B/clk an SM ingests from L2 and the 128 B/clk shared-memory port (UMMA operand
+// reads + TMA fills), plus the accumulator drain that is exposed when the tile needs all of TMEM.
+bool make_plan(Plan& pl, int bn, int nsub, int stationary, int n, int k, long long m, bool geglu, bool has_res, int pairs) {
+  const int tile_cols = bn * nsub;
+  const int num_k_blocks = (k + BK - 1) / BK;
+  const int num_m_blocks = (int)((m + 2 * BM - 1) / (2 * BM));
+  pl.bn = bn;
+  pl.nsub = nsub;
+  pl.stationary = stationary;
+  pl.acc_stages = tile_cols <= 256 ? 2 : 1;
+  pl.num_n_blocks = n / tile_cols;
+  const size_t b_stride = (size_t)(bn / 2) * BK * 2;  // bn % 16 == 0 -> multiple of 1024
+  pl.bres_bytes = stationary ? (size_t)num_k_blocks * nsub * b_stride : 0;
+  pl.stage_bytes = kABytes + (stationary ? 0 : (size_t)nsub * b_stride);
+  const size_t budget = kSmemBudget - (size_t)kEpiWarps * (has_res ? kMaxSlots : 2) * kSlotBytes;
+  if (pl.bres_bytes + 3 * pl.stage_bytes > budget) return false;
+  pl.stages = (int)((budget - pl.bres_bytes) / pl.stage_bytes);
+  if (pl.stages > kMaxStages) pl.stages = kMaxStages;
+  const double steps = num_k_blocks * 4.0;
+  const double mma = tile_cols / 2.0;
+  const double fill = 4096.0 + (stationary ? 0.0 : tile_cols * 16.0);
+  const double ingest = fill / 40.0;
+  const double port = (4096.0 * nsub + tile_cols * 16.0 + fill) / 128.0;
+  double step = mma > ingest ? mma : ingest;
+  if (port > step) step = port;
+  const int out_cols = geglu ? bn / 2 : tile_cols;
+  const double drain = 500.0 + 300.0 * ((out_cols / 32 + kEpiParts - 1) / kEpiParts) * (geglu ? 2.0 : 1.0);
+  // with two accumulator stages the drain hides behind the next tile's MMAs unless it is longer than them
+  double tile = steps * step;
+  if (pl.acc_stages == 1) tile += drain;
+  else if (drain > tile) tile = drain;
+  tile += 150.0;
+  const long long tiles = (long long)num_m_blocks * pl.num_n_blocks;
+  const long long per_pair = (tiles + pairs - 1) / pairs;
+  double cost = per_pair * tile;
+  if (stationary) {
+    // every change of n-block inside a pair's range stalls on the B block reload
+    const double reload = (double)pl.bres_bytes / 40.0 + 1500.0;
+    const double changes = 1.0 + (double)pl.num_n_blocks / pairs;
+    cost += reload * changes;
   }
-  return on;
+  pl.cost = cost;
+  return true;
 }
 
 }  // namespace
@@ -549,6 +657,7 @@ extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, c
   CA_CHECK_ARG(m >= 0 && n > 0 && k > 0, "linear: bad sizes m=%lld n=%d k=%d", m, n, k);
   CA_CHECK_ARG(epilogue == CA_EPI_NONE || epilogue == CA_EPI_GEGLU, "linear: unknown epilogue %d", epilogue);
   const bool geglu = epilogue == CA_EPI_GEGLU;
+  CA_CHECK_ARG(!(geglu && residual), "linear: GEGLU with a residual is not supported");
   CA_CHECK_ARG(k % 8 == 0 && ldx % 8 == 0 && ldx >= k, "linear: k and ldx must be multiples of 8 (16-byte TMA rows)");
   CA_CHECK_ARG(n % (geglu ? 64 : 32) == 0, "linear: n=%d must be a multiple of %d", n, geglu ? 64 : 32);
   const int n_out = geglu ? n / 2 : n;
@@ -557,64 +666,51 @@ extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, c
   CA_CHECK_ARG(m < (1ll << 31), "linear: m too large");
   if (m == 0) return CA_OK;
 
+  const int pairs = sm_count() / 2;
+  // ---- choose the tiling: every (bn, nsub, stationary) that divides n and fits shared memory / TMEM, cheapest first ----
+  Plan best;
+  {
+    static const char* cfg_env = getenv("CA_GEMM_CFG");  // development aid: "bn,nsub,stationary"
+    int f_bn = 0, f_nsub = 0, f_stat = -1;
+    if (cfg_env) sscanf(cfg_env, "%d,%d,%d", &f_bn, &f_nsub, &f_stat);
+    const int unit = geglu ? 64 : 16;
+    for (int bn = 256; bn >= unit; bn -= unit) {
+      for (int nsub = 1; nsub <= (geglu ? 1 : 2); ++nsub) {
+        if (n % (bn * nsub) != 0 || bn * nsub > 512 || (bn * nsub) % 32 != 0) continue;  // epilogue boxes are 32 columns wide
+        if (nsub == 2 && bn * 2 <= 256) continue;  // one wider sub-tile does the same with fewer instructions
+        for (int stat = 0; stat <= 1; ++stat) {
+          if (f_bn && (bn != f_bn || nsub != f_nsub || (f_stat >= 0 && stat != f_stat))) continue;
+          Plan pl;
+          if (!make_plan(pl, bn, nsub, stat, n, k, m, geglu, residual != nullptr, pairs)) continue;
+          if (pl.cost < best.cost) best = pl;
+        }
+      }
+    }
+    CA_CHECK_ARG(best.bn > 0, "linear: cannot tile n=%d k=%d", n, k);
+  }
+
   PairParams p{};
-  p.m = m; p.n = n; p.k = k; p.geglu = geglu ? 1 : 0; p.n_out = n_out; p.has_res = residual ? 1 : 0;
-  int sms = sm_count();
-  const int pairs = sms / 2;
+  p.m = m; p.n = n; p.k = k;
+  p.bn = best.bn; p.nsub = best.nsub; p.stationary = best.stationary; p.acc_stages = best.acc_stages; p.stages = best.stages;
+  p.out_cols = geglu ? best.bn / 2 : best.bn * best.nsub;
   p.num_m_blocks = (int)((m + 2 * BM - 1) / (2 * BM));
   p.num_k_blocks = (k + BK - 1) / BK;
-  // accumulator columns per tile: as wide as divides n (<= 256), narrower when that leaves most pairs without a tile
-  {
-    static const int cap_env = getenv("CA_GEMM_BN") ? atoi(getenv("CA_GEMM_BN")) : 256;  // development aid
-    int cap = cap_env;
-    for (;;) {
-      const int bn = geglu ? 2 * pick_bn(n / 2, cap / 2) : pick_bn(n, cap);
-      CA_CHECK_ARG(bn >= 32, "linear: cannot tile n=%d", n);
-      p.bn = bn;
-      p.num_n_blocks = geglu ? (n / 2) / (bn / 2) : n / bn;
-      const long long tiles = (long long)p.num_m_blocks * p.num_n_blocks;
-      if (tiles * 2 > pairs || bn <= 64 || cap <= 64) break;  // enough tiles for more than half of the pairs
-      cap = bn - (geglu ? 64 : 32) > 64 ? bn - (geglu ? 64 : 32) : 64;
-    }
-  }
+  p.num_n_blocks = best.num_n_blocks;
   p.tiles = (long long)p.num_m_blocks * p.num_n_blocks;
-  p.bias = bias; p.y = y; p.ldy = ldy;
+  p.bias = bias; p.y = y; p.ldy = ldy; p.res = residual; p.ldr = ldr;
+  p.slots = residual ? kMaxSlots : 2;
   p.b_bytes = (uint32_t)(p.bn / 2) * BK * 2;
-  p.b_stride = (p.b_bytes + 1023) & ~1023u;
+  p.b_stride = p.b_bytes;
+  p.bres_bytes = (uint32_t)best.bres_bytes;
+  p.stage_bytes = (uint32_t)best.stage_bytes;
   // instruction descriptor (kind::f16): D=f32 [4,6)=1; A/B format [7,10)/[10,13): 1=bf16, 0=f16; A,B K-major (bits
   // 15,16 = 0); N>>3 at [17,23); M>>4 at [24,29)  (M = 256: the pair's tile)
   const uint32_t fmt = dtype == CA_BF16 ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+  const long long grid_pairs = pairs < p.tiles ? pairs : p.tiles;
+  const size_t smem = (size_t)p.bres_bytes + (size_t)p.stages * p.stage_bytes + (size_t)kEpiWarps * p.slots * kSlotBytes + 1024;
 
-  p.slots = residual ? kMaxSlots : 1;
-  const size_t slot_bytes = (size_t)kEpiWarps * p.slots * kSlotBytes;
-  const size_t budget = 227 * 1024 - 1024 /*alignment*/ - 1024 /*static*/ - slot_bytes;
-  // B-stationary: the pair keeps its [BN x K] block resident when that still leaves >= 4 A stages and every n-block
-  // gets at least one pair
-  const size_t bres = (size_t)p.num_k_blocks * p.b_stride;
-  p.stationary = gemm_stationary_allowed() && bres + 4 * kABytes <= budget && p.num_n_blocks <= pairs &&
-                 p.num_m_blocks >= 2 * (pairs / p.num_n_blocks);
-  long long grid_pairs;
-  if (p.stationary) {
-    p.bres_bytes = (uint32_t)bres;
-    p.stage_bytes = kABytes;
-    const int g = pairs / p.num_n_blocks;  // pairs per n-block
-    p.tile_step = (long long)g * p.num_n_blocks;
-    grid_pairs = pairs;  // pairs >= tile_step idle (fewer than num_n_blocks of them)
-    if (grid_pairs > p.tile_step) grid_pairs = p.tile_step;
-  } else {
-    p.bres_bytes = 0;
-    p.stage_bytes = kABytes + p.b_stride;
-    grid_pairs = pairs < p.tiles ? pairs : p.tiles;
-    p.tile_step = grid_pairs;
-  }
-  int stages = (int)((budget - p.bres_bytes) / p.stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  CA_CHECK_ARG(stages >= 2, "linear: tile does not fit shared memory");
-  p.stages = stages;
-  const size_t smem = (size_t)p.bres_bytes + (size_t)stages * p.stage_bytes + slot_bytes + 1024;
-
-  CUtensorMap mx, mw, mr;
+  CUtensorMap mx, mw, my, mr;
   const CUtensorMapDataType dt = dtype == CA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   {
     const uint64_t dims[2] = {(uint64_t)k, (uint64_t)m};
@@ -632,14 +728,19 @@ extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, c
   {
     const uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)m};
     const uint32_t box[2] = {32, 32};
-    const uint64_t sr[1] = {(uint64_t)(residual ? ldr : ldy) * 2};
+    const uint64_t sy[1] = {(uint64_t)ldy * 2}, sr[1] = {(uint64_t)(residual ? ldr : ldy) * 2};
+    if (!encode_tensor_map(&my, dt, 2, y, dims, sy, box, CU_TENSOR_MAP_SWIZZLE_64B)) return CA_ERR_CUDA;
     if (!encode_tensor_map(&mr, dt, 2, residual ? residual : y, dims, sr, box, CU_TENSOR_MAP_SWIZZLE_64B)) return CA_ERR_CUDA;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  {
+    static const int roles_low = getenv("CA_GEMM_ROLES_LOW") ? atoi(getenv("CA_GEMM_ROLES_LOW")) : 0;
+    static const int max_stages = getenv("CA_GEMM_STAGES") ? atoi(getenv("CA_GEMM_STAGES")) : kMaxStages;
+    p.roles_low = roles_low;
+    if (p.stages > max_stages) p.stages = max_stages;
+  }
   static long long* timing_buf = nullptr;
   static const bool timing_on = getenv("CA_GEMM_TIMING") != nullptr;
-  static const int dbg_env = getenv("CA_GEMM_DBG") ? atoi(getenv("CA_GEMM_DBG")) : 0;
-  p.dbg = dbg_env;
   if (timing_on) {
     if (!timing_buf) CA_CUDA(cudaMalloc(&timing_buf, 8 * 1024 * sizeof(long long)));
     CA_CUDA(cudaMemsetAsync(timing_buf, 0, 8 * 1024 * sizeof(long long), st));
@@ -659,22 +760,31 @@ extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, c
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CA_CUDA(cudaLaunchKernelEx(&cfg, kernel, mx, mw, mr, p));
+    CA_CUDA(cudaLaunchKernelEx(&cfg, kernel, mx, mw, my, mr, p));
     if (timing_on) {  // development aid: synchronous, prints the mean per-CTA cycle attribution of this launch
       static long long host[8 * 1024];
       CA_CUDA(cudaStreamSynchronize(st));
       CA_CUDA(cudaMemcpy(host, timing_buf, sizeof(host), cudaMemcpyDeviceToHost));
-      double s8[8] = {0}, lead = 0;
+      double s8[8] = {0};
       const int ctas = (int)(2 * grid_pairs);
       for (int c = 0; c < ctas; ++c)
         for (int j = 0; j < 8; ++j) s8[j] += (double)host[c * 8 + j];
-      lead = ctas / 2.0;
-      fprintf(stderr, "[ca_linear timing] m=%lld n=%d k=%d bn=%d stat=%d stages=%d tiles/pair=%.1f | mma loop %.0f clk, wait tmem_empty %.0f, wait full %.0f | "
-              "producer wait empty %.0f | epi part0 wait acc %.0f res %.0f | epi part1 wait acc %.0f res %.0f\n", m, n, k, p.bn, p.stationary, p.stages,
-              (double)p.tiles / (double)p.tile_step, s8[0] / lead, s8[1] / lead, s8[2] / lead, s8[3] / ctas, s8[4] / ctas, s8[5] / ctas, s8[6] / ctas, s8[7] / ctas);
+      const double lead = ctas / 2.0;
+      fprintf(stderr,
+              "[ca_linear timing] m=%lld n=%d k=%d bn=%dx%d stat=%d stages=%d acc=%d tiles/pair=%.1f | mma loop %.0f clk: wait "
+              "tmem_empty %.0f, full %.0f, bres %.0f | producer wait empty %.0f bres_empty %.0f | epi wait acc %.0f res %.0f\n",
+              m, n, k, p.bn, p.nsub, p.stationary, p.stages, p.acc_stages, (double)p.tiles / (double)grid_pairs, s8[0] / lead,
+              s8[1] / lead, s8[2] / lead, s8[5] / lead, s8[3] / ctas, s8[4] / ctas, s8[6] / ctas, s8[7] / ctas);
     }
     return CA_OK;
   };
-  if (dtype == CA_BF16) return run(gemm_pair_kernel<__nv_bfloat16>);
-  return run(gemm_pair_kernel<__half>);
+  const int epi = geglu ? EPI_GEGLU : (residual ? EPI_RES : EPI_BIAS);
+  if (dtype == CA_BF16) {
+    if (epi == EPI_GEGLU) return run(gemm_pair_kernel<__nv_bfloat16, EPI_GEGLU>);
+    if (epi == EPI_RES) return run(gemm_pair_kernel<__nv_bfloat16, EPI_RES>);
+    return run(gemm_pair_kernel<__nv_bfloat16, EPI_BIAS>);
+  }
+  if (epi == EPI_GEGLU) return run(gemm_pair_kernel<__half, EPI_GEGLU>);
+  if (epi == EPI_RES) return run(gemm_pair_kernel<__half, EPI_RES>);
+  return run(gemm_pair_kernel<__half, EPI_BIAS>);
 }

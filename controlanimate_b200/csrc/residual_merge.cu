@@ -73,7 +73,7 @@ __device__ __forceinline__ void merge_body(const MergeParams& p, const MergeTens
     if (p.add) {
 #pragma unroll
       for (int u = 0; u < kVecPerThread; ++u)
-        if (ok[u]) draw[u] = ldg_stream(reinterpret_cast<const uint4*>(t.dst) + idx[u]);
+        if (ok[u]) draw[u] = ldg_stream_rw(reinterpret_cast<const uint4*>(t.dst) + idx[u]);  // dst is written below: no .nc
     }
 #pragma unroll
     for (int u = 0; u < kVecPerThread; ++u) {

@@ -116,27 +116,24 @@ def conv_bias(conv: nn.Conv2d, x4: torch.Tensor, *, silu: bool = False, residual
         y = y + conv.bias.to(y.dtype).view(1, -1, 1, 1) if conv.bias is not None else y
         y = F.silu(y) if silu else y
         return y if residual is None else y + residual
-    bias = sum_f32(conv.bias, extra_bias) if extra_bias is not None else f32(conv.bias)
+    bias = sum_f32(conv, conv.bias, extra_bias) if extra_bias is not None else f32(conv.bias)
     return ops.bias_act_residual(y, bias, residual, silu=silu, inplace=True)
 
 
-class _BiasSum:
-    """fp32 sum of small parameter vectors, cached until one of them changes."""
-    cache = {}
-
-
-def sum_f32(*ps: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+def sum_f32(owner: nn.Module, *ps: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """fp32 sum of small parameter vectors (folded biases), cached ON THE OWNING MODULE until one of them changes —
+    the cache dies with the module, so a recycled id()/address of a later model can never hit a stale entry."""
     ps = [p for p in ps if p is not None]
     if not ps:
         return None
     key = tuple((id(p), p._version, p.data_ptr(), p.device) for p in ps)
-    hit = _BiasSum.cache.get(key[0][0])
-    if hit is None or hit[0] != key:
+    hit = owner.__dict__.get("_ca_bias_sum")
+    if hit is None or hit[0] != key or any(a is not b for a, b in zip(hit[2], ps)):
         total = ps[0].detach().float()
         for p in ps[1:]:
             total = total + p.detach().float()
-        hit = (key, total.contiguous())
-        _BiasSum.cache[key[0][0]] = hit
+        hit = (key, total.contiguous(), tuple(ps))   # holding the params keeps their id()s unique while cached
+        owner.__dict__["_ca_bias_sum"] = hit
     return hit[1]
 
 
@@ -197,8 +194,18 @@ class B200TemporalAttnProcessor(nn.Module):
         super().__init__()
         self._qkv = _FusedWeights()
 
+    @staticmethod
+    def _is_self(hidden_states, encoder_hidden_states) -> bool:
+        """VersatileAttention.forward (motion_module.py:309,321) never passes None: for self-attention it hands the
+        processor `encoder_hidden_states = hidden_states`.  Same object, or the same memory viewed the same way, is
+        self-attention; anything else is a genuine context this processor does not implement."""
+        e = encoder_hidden_states
+        return e is None or e is hidden_states or (
+            e.data_ptr() == hidden_states.data_ptr() and e.shape == hidden_states.shape
+            and e.stride() == hidden_states.stride() and e.dtype == hidden_states.dtype)
+
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
-        if encoder_hidden_states is not None or attention_mask is not None:
+        if not self._is_self(hidden_states, encoder_hidden_states) or attention_mask is not None:
             raise ValueError("B200TemporalAttnProcessor handles temporal SELF-attention without a mask only")
         for name in ("spatial_norm", "group_norm", "norm_cross"):
             if getattr(attn, name, None) is not None:
@@ -438,7 +445,7 @@ class B200ResnetBlock3D(nn.Module):
             # 1x1 shortcut == token GEMM whose epilogue adds both biases and conv2's output   :213-216
             n, _, hh, ww = x4.shape
             w2 = self.conv_shortcut.weight.reshape(self.out_channels, self.in_channels)
-            y = ops.linear(tokens(x4), w2, sum_f32(self.conv_shortcut.bias, self.conv2.bias), residual=tokens(h))
+            y = ops.linear(tokens(x4), w2, sum_f32(self, self.conv_shortcut.bias, self.conv2.bias), residual=tokens(h))
             return from_tokens(y, n, hh, ww)
         if self.conv_shortcut is not None:
             x4 = conv_bias(self.conv_shortcut, x4)

@@ -98,6 +98,9 @@ class ControlNetParallel:
     apply the per-net scales and reduce in fp32 at the consumer (exact up to summation order)."""
 
     def __init__(self, rank: int, world: int, n_nets: int, group=None):
+        if world > n_nets:
+            raise ValueError(f"ControlNet sharding needs world <= n_nets (got {world} ranks for {n_nets} nets): a rank "
+                             "without a net has no residual shapes to contribute")
         self.rank, self.world, self.n_nets, self.group = rank, world, n_nets, group
 
     def my_nets(self) -> List[int]:

@@ -119,29 +119,63 @@ class DenoisingLoop:
             noise = u + self.guidance_scale * (c - u)                                                    # :845-846
         return noise
 
+    def invalidate_graphs(self):
+        """Drop every captured graph (call after swapping modules, e.g. install() / set_ip_adapter)."""
+        self._graphs.clear()
+        self._params = None
+
+    def _weight_stamp(self):
+        """Cheap identity of every weight the captured graph baked in (device pointers of the parameters and of their
+        cached fp32 / fused / channels_last copies follow from these): storage pointers + in-place version counters."""
+        if getattr(self, "_params", None) is None:
+            mods = [self.unet] + (list(self.controlnets.controlnets) if self.controlnets is not None else [])
+            self._params = [p for m in mods for p in list(m.parameters()) + list(m.buffers())]
+        return hash(tuple(p.data_ptr() for p in self._params)), sum(p._version for p in self._params)
+
     def _graphed_noise(self, latents, t: int, prompt_embeds):
-        key = (tuple(latents.shape), latents.dtype, tuple(prompt_embeds.shape), prompt_embeds.dtype, latents.device)
+        mc = self.controlnets
+        images = list(mc.prep_images) if mc is not None and mc.prep_images is not None else []
+        # everything the captured kernels read by value or by baked-in pointer is part of the key: shapes, the scalars of
+        # the step, and the weights; the per-window control images are copied into graph-owned buffers before a replay
+        key = (tuple(latents.shape), latents.dtype, tuple(prompt_embeds.shape), prompt_embeds.dtype, latents.device,
+               float(self.guidance_scale), bool(self.guess_mode), tuple(mc.cond_scale) if mc is not None else (),
+               bool(mc.lazy) if mc is not None else None, tuple((tuple(im.shape), im.dtype) for im in images),
+               self._weight_stamp())
         g = self._graphs.get(key)
         if g is None:
+            if len(self._graphs) >= 4:          # stale captures pin their private memory pools
+                self._graphs.clear()
             s_lat, s_prompt = latents.clone(), prompt_embeds.clone()
+            s_images = [im.clone() for im in images]
             s_t = torch.full((1,), int(t), dtype=torch.int64, device=latents.device)
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):                # warm-up: cuDNN algorithm selection, caches, workspaces
-                for _ in range(2):
-                    self.predict_noise(s_lat, s_t, s_prompt)
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                s_out = self.predict_noise(s_lat, s_t, s_prompt)
-            g = self._graphs[key] = (graph, s_lat, s_t, s_prompt, s_out)
-        graph, s_lat, s_t, s_prompt, s_out = g
-        s_lat.copy_(latents, non_blocking=True)
-        if prompt_embeds.data_ptr() != s_prompt.data_ptr():
-            s_prompt.copy_(prompt_embeds, non_blocking=True)
-        s_t.fill_(int(t))
-        graph.replay()
-        return s_out
+            if mc is not None:
+                mc.prep_images = s_images
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):                # warm-up: cuDNN algorithm selection, caches, workspaces
+                    for _ in range(2):
+                        self.predict_noise(s_lat, s_t, s_prompt)
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    s_out = self.predict_noise(s_lat, s_t, s_prompt)
+            finally:
+                if mc is not None:
+                    mc.prep_images = images if images else None
+            g = self._graphs[key] = dict(graph=graph, lat=s_lat, t=s_t, prompt=s_prompt, out=s_out, images=s_images,
+                                         seen=[None] * len(s_images))
+        g["lat"].copy_(latents, non_blocking=True)
+        if prompt_embeds.data_ptr() != g["prompt"].data_ptr():
+            g["prompt"].copy_(prompt_embeds, non_blocking=True)
+        for k, im in enumerate(images):      # the reference re-runs prep_control_images for every window (pipeline :226-273)
+            ident = (im.data_ptr(), im._version)
+            if g["seen"][k] != ident:
+                g["images"][k].copy_(im, non_blocking=True)
+                g["seen"][k] = ident
+        g["t"].fill_(int(t))
+        g["graph"].replay()
+        return g["out"]
 
     @torch.no_grad()
     def step(self, latents: torch.Tensor, t: int, prompt_embeds: torch.Tensor) -> torch.Tensor:

@@ -27,6 +27,11 @@ import torch.nn.functional as F
 
 Tensor = torch.Tensor
 
+# When True, attention_core dispatches to F.scaled_dot_product_attention — what the reference's own
+# `AttnProcessor2_0` does (modules/attention_processor.py:247-256).  Only the GPU-eager yardstick of bench.py flips it
+# (the explicit softmax below would materialise a 4096 x 4096 score matrix per head and frame); parity tests keep False.
+USE_SDPA = False
+
 
 # ----------------------------------------------------------------------------------------------
 # kernel (2): GroupNorm + SiLU (+ time-embedding add)
@@ -98,8 +103,11 @@ def attention_core(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: Optional[
     qh = q.reshape(B, S, heads, hd).transpose(1, 2)
     kh = k.reshape(B, k.shape[1], heads, hd).transpose(1, 2)
     vh = v.reshape(B, v.shape[1], heads, hd).transpose(1, 2)
-    p = torch.softmax(torch.matmul(qh, kh.transpose(-1, -2)) * scale, dim=-1)
-    o = torch.matmul(p, vh)
+    if USE_SDPA:
+        o = F.scaled_dot_product_attention(qh, kh, vh, scale=scale)
+    else:
+        p = torch.softmax(torch.matmul(qh, kh.transpose(-1, -2)) * scale, dim=-1)
+        o = torch.matmul(p, vh)
     return o.transpose(1, 2).reshape(B, S, C)
 
 

@@ -27,13 +27,14 @@ Tensor = torch.Tensor
 def timestep_embedding(timesteps: Tensor, dim: int, flip_sin_to_cos: bool = True, freq_shift: float = 0.0) -> Tensor:
     """diffusers `Timesteps`: [cos, sin] halves when flip_sin_to_cos."""
     half = dim // 2
-    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / (half - freq_shift))
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=timesteps.device) / (half - freq_shift))
     e = timesteps[:, None].float() * freqs[None]
     s, c = torch.sin(e), torch.cos(e)
     return torch.cat([c, s], -1) if flip_sin_to_cos else torch.cat([s, c], -1)
 
 
 def time_embedding(sd: Dict[str, Tensor], t_emb: Tensor, cond: Optional[Tensor] = None, prefix="time_embedding.") -> Tensor:
+    t_emb = t_emb.to(sd[prefix + "linear_1.weight"].dtype)      # unet.py:532 `t_emb.to(dtype=self.dtype)` (identity in fp32)
     if cond is not None:
         t_emb = t_emb + F.linear(cond, sd[prefix + "cond_proj.weight"])
     h = F.linear(t_emb, sd[prefix + "linear_1.weight"], sd[prefix + "linear_1.bias"])
@@ -96,7 +97,7 @@ def unet3d_forward(sd: Dict[str, Tensor], cfg: dict, sample: Tensor, timestep, e
     upf = 2 ** (len(boc) - 1)
     forward_upsample_size = any(s % upf != 0 for s in sample.shape[-2:])                     # :491-499
 
-    ts = torch.as_tensor(timestep).reshape(-1).expand(b)                                     # :510-524
+    ts = torch.as_tensor(timestep, device=sample.device).reshape(-1).expand(b)               # :510-524
     emb = time_embedding(sd, timestep_embedding(ts, boc[0]), timestep_cond)                  # :526-534
 
     x = R.conv2d_per_frame(sample, sd["conv_in.weight"], sd["conv_in.bias"])                 # :547
@@ -169,7 +170,7 @@ def controlnet_forward(sd: Dict[str, Tensor], cfg: dict, sample: Tensor, timeste
     lpb = cfg["layers_per_block"]
     groups, eps, heads = cfg["norm_num_groups"], cfg["norm_eps"], cfg["attention_head_dim"]
     n = sample.shape[0]
-    ts = torch.as_tensor(timestep).reshape(-1).expand(n)
+    ts = torch.as_tensor(timestep, device=sample.device).reshape(-1).expand(n)
     emb = time_embedding(sd, timestep_embedding(ts, boc[0]))
 
     def v(x):  # [n,c,h,w] -> [n,c,1,h,w] so the per-frame 3-D helpers apply with f = 1

@@ -326,6 +326,9 @@ LINEAR_CASES = [
     (256, 64, 64), (128, 320, 320), (1000, 960, 320), (4096, 640, 640), (2048, 1280, 2560), (77, 192, 128), (300, 2560, 320),
     # large-m cases: the CTA-pair kernel switches to its B-stationary schedule (K = 320) / many tiles per pair
     (8000, 960, 320), (9001, 2560, 320), (19000, 320, 320), (5000, 320, 1280),
+    # round 2 tilings: contiguous tile ranges that straddle n-blocks with a resident B block
+    # (bn = 240); 512-column single-stage tiles (two UMMA sub-tiles per A stage) for long K with narrow N
+    (3000, 96, 64), (1500, 160, 320), (40000, 1920, 640), (33000, 640, 2560), (70000, 320, 1280), (20000, 1280, 1280),
 ]
 
 
