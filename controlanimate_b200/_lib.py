@@ -9,7 +9,7 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libca_b200.so")
+LIB_PATH = os.environ.get("CA_LIB_PATH") or os.path.join(HERE, "libca_b200.so")   # CA_LIB_PATH: development builds only
 
 CA_BF16, CA_F16, CA_F32 = 0, 1, 2
 CA_LAYOUT_NCFHW, CA_LAYOUT_BFHWC = 0, 1

@@ -1,8 +1,6 @@
-S="qkv m8192,geglu m8192,qkv m131072,proj_in m8192"
-run() { name=$1; shift; env "$@" timeout 120 python scripts/gemm_lab.py $name "$S" 2>&1 | grep -v "^$"; env "$@" CA_GEMM_TIMING=1 timeout 120 python scripts/gemm_lab.py $name "$S" 2>&1 | grep "timing\]" | awk 'NR%2==0' | sed 's/\[ca_linear timing\] //'; }
-run A CA_GEMM_CFG=256,1,0
-run B CA_GEMM_CFG=256,1,0 CA_GEMM_ROLES_LOW=1
-run C CA_GEMM_CFG=256,1,0 CA_GEMM_STAGES=6
-run D CA_GEMM_CFG=256,1,0 CA_GEMM_VEC32=0
-run E CA_GEMM_CFG=240,1,0
-run F CA_GEMM_CFG=240,1,0 CA_GEMM_ROLES_LOW=1
+( time timeout 1500 python -m pytest tests -m gpu -q -x ) > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+LAB_CUBLAS=1 timeout 200 python scripts/gemm_lab.py final > gpurun_out/lab_final.log 2>&1
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
+echo "bench exit $?" >> gpurun_out/bench.err
+tail -5 gpurun_out/pytest_gpu.log; cut -c1-300 gpurun_out/bench.json; tail -3 gpurun_out/bench.err

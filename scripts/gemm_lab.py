@@ -38,7 +38,22 @@ for T, c in ((131072, 320), (32768, 640), (8192, 1280), (2048, 1280)):
             e0.record(); fn(); e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e3)
         us = statistics.median(ts)
+        tc = []
+        if os.environ.get('LAB_CUBLAS'):
+            F = torch.nn.functional
+            def cub():
+                if geglu:
+                    a_, g_ = F.linear(x, w, bias.to(bt)).chunk(2, dim=-1); return a_ * F.gelu(g_)
+                if res: return torch.addmm(r, x, w.t()).add_(bias.to(bt))
+                return F.linear(x, w, bias.to(bt))
+            cub(); torch.cuda.synchronize()
+            for _ in range(10):
+                flush.fill_(1.0); flush[: flush.numel() // 2].sum(); torch.cuda._sleep(300000)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); cub(); e1.record(); torch.cuda.synchronize()
+                tc.append(e0.elapsed_time(e1) * 1e3)
         row = dict(tag=tag, shape=f"{nm} m{T} n{n} k{k}", us=round(us, 1), tflops=round(2.0 * T * n * k / us / 1e6, 0))
+        if tc: row['cublas_fused_us'] = round(statistics.median(tc), 1)
         rows.append(row); print(json.dumps(row), flush=True)
         del x, w, r, y
 if rows:
