@@ -9,8 +9,14 @@ UNet3D -> CFG -> DDIM, reference controlanimation_pipeline.py:793-849); frames/s
   python bench.py [--gpus N] [--steps K] [--warmup W]            # this framework (sm_100a kernels)
   python bench.py --impl reference ...                           # CPU arm: the oracle restatement of the reference's
                                                                  # own PyTorch path on the host cores (bounded sample)
-N > 1 (torchrun): every rank denoises its own 16-frame window of one long clip (windows overlap by 4 latent frames,
-exchanged and blended each step with NCCL send/recv) -> weak scaling, value = N * 16 / (20 * step time).
+N > 1 (torchrun), --parallelism:
+  windows (default)  every rank denoises its own 16-frame window of one long clip (windows overlap by 4 latent frames,
+                     exchanged and blended each step with NCCL send/recv) -> weak scaling; value counts the UNIQUE frames of the
+                     clip (N * 16 - (N - 1) * 4), `frames_counted_per_s` also the overlap frames every neighbour denoises twice
+  cfg                N = 2: one window, each rank one CFG row (strong scaling: step latency)
+  cfg+controlnet     N = 4, 6: CFG halves x (UNet rank + ControlNet ranks); the ControlNet ranks' raw residuals are read over
+                     NVLink by kernel (3) on the UNet rank (symmetric memory), overlapping the UNet's down path
+  controlnet         N = 2, 3: UNet rank + ControlNet ranks (no CFG split)
 """
 from __future__ import annotations
 
@@ -97,9 +103,11 @@ class ClockSampler:
 # reference arm / cpu_baseline: the oracle (CPU restatement of the reference's PyTorch path)
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_step_factory(frames_sample: int, latent: int, n_nets: int = 2, seed: int = 0):
-    """Return (step_fn, description).  One denoising step of config 2 restricted to `frames_sample` frames at full
-    resolution: frames are independent everywhere except the (tiny) temporal attention, so frames/step-second of the
-    sample is the per-frame throughput of the full 16-frame step."""
+    """Return (step_fn, description, kind).  One denoising step of config 2 restricted to `frames_sample` (>= 4, so that the
+    temporal attention is real) of the 16 frames at full resolution.  The UNet3D is the REFERENCE'S OWN module
+    (animatediff/models/unet.py through oracle/diffusers_shim, shipped under baseline/_ref by build()) when it can be
+    imported, else the oracle port; the ControlNets are diffusers code (third party, absent) -> always the oracle port."""
+    from oracle import ref_import
     from oracle import ref_ops as R
     from oracle import ref_unet3d as U
     from oracle import synth
@@ -125,6 +133,24 @@ def cpu_reference_step_factory(frames_sample: int, latent: int, n_nets: int = 2,
 
     sd_u = fill(U.unet3d_shapes(cfg))
     sd_c = [fill(U.controlnet_shapes(cfg)) for _ in range(n_nets)]
+    ref_unet, kind = None, "port"
+    try:
+        ref_import.import_reference()
+        from animatediff.models.unet import UNet3DConditionModel          # the reference's own class
+        from modules.attention_processor import AttnProcessor2_0
+        with torch.device("meta"):
+            ref_unet = UNet3DConditionModel(**cfg)
+        ref_unet = ref_unet.to_empty(device="cpu")
+        missing = ref_unet.load_state_dict(sd_u, strict=False)            # strays: BasicTransformerBlock's unused Attention params
+        with torch.no_grad():
+            for k in missing.missing_keys:
+                ref_unet.state_dict()[k].zero_()
+        ref_unet.set_attn_processor(AttnProcessor2_0())
+        ref_unet.eval()
+        kind = "reference"
+    except Exception as e:  # noqa: BLE001 - the port is the documented fallback
+        sys.stderr.write(f"[bench] reference modules unavailable ({type(e).__name__}: {e}); timing the oracle port\n")
+        ref_unet = None
     f = frames_sample
     latents = torch.randn(1, 4, f, latent, latent, generator=gen)
     prompt = torch.randn(2, 77, 768, generator=gen)
@@ -141,12 +167,18 @@ def cpu_reference_step_factory(frames_sample: int, latent: int, n_nets: int = 2,
         ctx = torch.cat([prompt] * f)
         per_net = [U.controlnet_forward(sd_c[k], cfg, x2d, t, ctx, images[k]) for k in range(n_nets)]
         down, mid = R.merge_controlnet_residuals(per_net, COND_SCALE[:n_nets], f)
-        noise = U.unet3d_forward(sd_u, cfg, model_in, t, prompt, down, mid)
+        if ref_unet is not None:
+            noise = ref_unet(model_in, t, encoder_hidden_states=prompt, down_block_additional_residuals=down,
+                             mid_block_additional_residual=mid).sample
+        else:
+            noise = U.unet3d_forward(sd_u, cfg, model_in, t, prompt, down, mid)
         state["latents"] = R.ddim_step(R.cfg_combine(noise, GUIDANCE), t, lat, acp, DDIM_STEPS)
 
-    desc = (f"oracle (torch fp32 CPU restatement of the reference path), one denoising step of config 2 on {f} of {FRAMES} frames "
-            f"at full 512x512 (latent {latent}x{latent}), b=2 CFG, {n_nets} ControlNets; frames/s = {f}/(20*step_s)")
-    return step, desc
+    what = ("the reference's own UNet3DConditionModel (animatediff/models/unet.py via oracle/diffusers_shim, AttnProcessor2_0) + oracle-port "
+            "ControlNets (diffusers, third party)") if kind == "reference" else "oracle port (torch fp32 CPU restatement of the reference path)"
+    desc = (f"{what}, fp32, one denoising step of config 2 on {f} of {FRAMES} frames at full 512x512 (latent {latent}x{latent}), b=2 CFG, "
+            f"{n_nets} ControlNets; frames/s = {f}/(20*step_s)")
+    return step, desc, kind
 
 
 def run_reference(args):
@@ -154,7 +186,7 @@ def run_reference(args):
     if rank != 0:
         return
     f = args.cpu_frames
-    step, desc = cpu_reference_step_factory(f, args.latent)
+    step, desc, kind = cpu_reference_step_factory(f, args.latent)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -167,7 +199,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, parallelism="cpu"),
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -181,13 +213,75 @@ def workload_config(args, parallelism):
             "l2": "per-step working set (>10 GB of activations and 4 GB of weights) exceeds the 126 MB L2; no explicit flush"}
 
 
+def torch_eager_yardstick(dev, latent, frames=FRAMES, steps=2):
+    """The reference's op sequence under stock PyTorch on the same GPU (SURVEY §2.1's B200 bar): the oracle restatement run
+    in bf16 on CUDA with F.scaled_dot_product_attention (what the reference's AttnProcessor2_0 dispatches to), cuDNN
+    convolutions, native GroupNorm / LayerNorm arithmetic, one launch per op.  A yardstick under `extra`, never the
+    reference arm and never a product path."""
+    from oracle import ref_ops as R
+    from oracle import ref_unet3d as U
+    from oracle import synth
+    cfg = synth.unet_config(tiny=False)
+    gen = torch.Generator(device=dev).manual_seed(7)
+
+    def fill(shapes):
+        sd = {}
+        for k, shp in shapes.items():
+            if k.endswith(".pe"):
+                sd[k] = R.positional_encoding(shp[1], shp[2]).to(dev)
+            elif len(shp) >= 2:
+                fan_in = 1
+                for v in shp[1:]:
+                    fan_in *= v
+                sd[k] = (torch.randn(shp, generator=gen, device=dev) * fan_in ** -0.5).bfloat16()
+            elif k.endswith("weight") and "norm" in k:
+                sd[k] = (1 + 0.1 * torch.randn(shp, generator=gen, device=dev)).bfloat16()
+            else:
+                sd[k] = (0.1 * torch.randn(shp, generator=gen, device=dev)).bfloat16()
+        return sd
+
+    sd_u, sd_c = fill(U.unet3d_shapes(cfg)), [fill(U.controlnet_shapes(cfg)) for _ in range(2)]
+    f = frames
+    lat = torch.randn(1, 4, f, latent, latent, generator=gen, device=dev).bfloat16()
+    prompt = torch.randn(2, 77, 768, generator=gen, device=dev).bfloat16()
+    images = [torch.randn(2 * f, 3, latent * 8, latent * 8, generator=gen, device=dev).bfloat16() for _ in range(2)]
+    acp, t = R.ddim_alphas_cumprod().to(dev), R.ddim_timesteps(DDIM_STEPS)[0]
+
+    @torch.no_grad()
+    def step(x):
+        model_in = torch.cat([x] * 2)
+        x2d = model_in.permute(0, 2, 1, 3, 4).reshape(2 * f, 4, latent, latent)
+        ctx = torch.cat([prompt] * f)
+        per_net = [U.controlnet_forward(sd_c[k], cfg, x2d, t, ctx, images[k]) for k in range(2)]
+        down, mid = R.merge_controlnet_residuals(per_net, COND_SCALE, f)
+        noise = U.unet3d_forward(sd_u, cfg, model_in, t, prompt, down, mid)
+        return R.ddim_step(R.cfg_combine(noise.float(), GUIDANCE), t, x.float(), acp, DDIM_STEPS).bfloat16()
+
+    R.USE_SDPA = True
+    try:
+        lat = step(lat)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            lat = step(lat)
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        R.USE_SDPA = False
+    ms = e0.elapsed_time(e1) / steps
+    del sd_u, sd_c
+    torch.cuda.empty_cache()
+    return {"ms_per_step": ms, "frames_per_s": f / (DDIM_STEPS * ms * 1e-3),
+            "what": "oracle port of the reference path in bf16 on this GPU, stock PyTorch eager (cuBLAS, cuDNN, SDPA), same workload"}
+
+
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch.distributed as dist
-    from controlanimate_b200 import _lib, ops, parallel, pipeline, profiler, unet as un, utils
-    from oracle import synth
+    from controlanimate_b200 import _lib, parallel, pipeline, profiler, unet as un, utils
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -203,18 +297,21 @@ def run_b200(args):
         raise SystemExit(f"sm_{lib.ca_device_sm()} device: these kernels are sm_100a only")
     torch.backends.cudnn.benchmark = True
 
-    cfg = synth.unet_config(tiny=False)
+    mode = args.parallelism if world > 1 else "single"
+    cfg = utils.sd15_unet3d_config()
     dtype = torch.bfloat16
     unet = utils.build_on_device(lambda: un.UNet3DConditionModel(**cfg), dev, dtype, seed=1)
     nets = [utils.build_on_device(lambda: un.ControlNetModel(), dev, dtype, seed=2 + k) for k in range(2)]
     mc = pipeline.MultiControlNetResiduals(nets, COND_SCALE)
     sched = pipeline.DDIMScheduler()
     timesteps = sched.set_timesteps(DDIM_STEPS)
-    loop = pipeline.DenoisingLoop(unet, mc, sched, guidance_scale=GUIDANCE, use_cuda_graph=not args.no_graph)
-    windows = parallel.WindowParallel(rank, world, FRAMES, OVERLAP) if world > 1 else None
+    step_par = parallel.StepParallel(mode, rank, world, n_nets=2) if mode in parallel.StepParallel.MODES else None
+    loop = pipeline.DenoisingLoop(unet, mc, sched, guidance_scale=GUIDANCE, use_cuda_graph=not args.no_graph, parallel=step_par)
+    windows = parallel.WindowParallel(rank, world, FRAMES, OVERLAP) if mode == "windows" else None
 
     f, lat = FRAMES, args.latent
-    g = torch.Generator(device="cpu").manual_seed(100 + rank)
+    # windows: every rank has its own window of the clip; step parallelism: every rank works on THE SAME window
+    g = torch.Generator(device="cpu").manual_seed(100 + (rank if mode == "windows" else 0))
     # host-side inputs (pinned): what a caller of the public API holds
     h_latents = torch.randn(1, 4, f, lat, lat, generator=g).pin_memory()
     h_prompt = torch.randn(2, 77, 768, generator=g).to(dtype).pin_memory()
@@ -284,46 +381,58 @@ def run_b200(args):
         ms, ms_e2e = float(tms[0]), float(tms[1])
 
     # ---- per-kernel timing pass (CUDA events around every C-ABI launch, on the launching stream) ---------------
-    kern = None
-    if rank == 0:
-        loop.use_cuda_graph = False                # eager: every launch bracketed by events, GPU kept backlogged
-        lat2 = loop.step(latents, timesteps[0], d_prompt)
-        torch.cuda.synchronize()
-        profiler.enable(True, backlog_ms=400.0)
-        lat2 = loop.step(lat2, timesteps[1], d_prompt)
-        torch.cuda.synchronize()
-        kern = profiler.summary(measured_peaks())
-        profiler.enable(False)
-        # shares are of the TIMED (graph-replayed) step, not of the instrumented pass whose wall clock holds the backlog
-        for fam in kern["families"].values():
-            fam["share_of_step"] = fam["ms_total"] / ms
-        kern["dominant"]["share_of_step"] = kern["families"][kern["dominant"]["kernel"]]["share_of_step"]
-        kern["own_share"] = sum(fam["ms_total"] for fam in kern["families"].values()) / ms
-        if args.torch_profile:
-            # attribution aid (never a bench value): which aten ops the non-library, non-own kernels of one eager step come from
-            from torch.profiler import ProfilerActivity, profile
-            with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
-                lat2 = loop.step(lat2, timesteps[2], d_prompt)
-                torch.cuda.synchronize()
-            with open(args.torch_profile, "w") as fh:
-                fh.write(prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=120,
-                                                                             max_name_column_width=60, max_shapes_column_width=90))
+    # every rank runs it (the step contains collectives when N > 1); rank 0 reports its own kernels
+    loop.use_cuda_graph = False                # eager: every launch bracketed by events, GPU kept backlogged
+    lat2 = one_step(latents, 0)
+    torch.cuda.synchronize()
+    profiler.enable(True, backlog_ms=400.0)
+    lat2 = one_step(lat2, 1)
+    torch.cuda.synchronize()
+    kern = profiler.summary(measured_peaks())
+    profiler.enable(False)
+    # shares are of the TIMED (graph-replayed) step, not of the instrumented pass whose wall clock holds the backlog
+    for fam in kern["families"].values():
+        fam["share_of_step"] = fam["ms_total"] / ms
+    kern["dominant"]["share_of_step"] = kern["families"][kern["dominant"]["kernel"]]["share_of_step"]
+    kern["own_share"] = sum(fam["ms_total"] for fam in kern["families"].values()) / ms
+    if rank == 0 and args.torch_profile and world == 1:
+        # attribution aid (never a bench value): which aten ops the non-library, non-own kernels of one eager step come from
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
+            lat2 = loop.step(lat2, timesteps[2], d_prompt)
+            torch.cuda.synchronize()
+        with open(args.torch_profile, "w") as fh:
+            fh.write(prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=120,
+                                                                         max_name_column_width=60, max_shapes_column_width=90))
+    barrier()
 
     if rank == 0:
         peaks = measured_peaks()
-        value = world * f / (DDIM_STEPS * ms * 1e-3)
-        e2e = world * f / (DDIM_STEPS * ms_e2e * 1e-3)
+        if mode == "windows" or world == 1:
+            unique = world * f - (world - 1) * OVERLAP          # adjacent windows share OVERLAP frames
+            counted = world * f
+            scaling = "weak"
+            par_desc = "single" if world == 1 else f"frame-windows x{world} (overlap {OVERLAP}: {unique} unique frames of {counted} denoised)"
+        else:
+            unique = counted = f                                # one window, split over the ranks
+            scaling = "strong"
+            par_desc = {"cfg": "CFG halves x2 (one window)", "controlnet": f"UNet rank + {world - 1} ControlNet rank(s) (one window)",
+                        "cfg+controlnet": f"CFG halves x (UNet rank + {world // 2 - 1} ControlNet rank(s)) (one window)"}[mode]
+        value = unique / (DDIM_STEPS * ms * 1e-3)
+        e2e = unique / (DDIM_STEPS * ms_e2e * 1e-3)
         top = kern["dominant"]
         top["traffic"] = ncu_traffic(top["kernel"])
         top["traffic_source"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu launch list of the same step (profiles/)"
         line = {
             "metric": "denoised frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(args, parallelism="single" if world == 1 else f"frame-windows x{world} (overlap {OVERLAP})"),
+            "config": workload_config(args, parallelism=par_desc),
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h_latents.numel() * 4 + h_prompt.numel() * 2, "d2h_bytes_per_step": h_out.numel() * 4},
+            "frames_unique": unique, "frames_counted": counted,
+            "frames_counted_per_s": counted / (DDIM_STEPS * ms * 1e-3),
             # kernels of libca_b200.so executed inside the timed region (counted per launch in eager mode; with CUDA-graph
             # replay = launches recorded in one captured step x timed steps)
             "gpu_launches": launches if launches else kern["launches_per_step"] * args.steps,
@@ -333,16 +442,32 @@ def run_b200(args):
             "own_kernel_share_of_step": kern["own_share"],
             "peaks": peaks,
         }
-        if args.cpu_baseline:
-            step, desc = cpu_reference_step_factory(args.cpu_frames, args.latent)
-            step()
+        if step_par is not None and step_par.g > 1:
+            # bytes kernel (3) pulls over NVLink per step on each UNet rank: the raw residual sets of the sharded ControlNets
+            rows = (1 if step_par.halves == 2 else 2) * f
+            per_net = sum(c * (lat // d) * (lat // d) for c, d in ((320, 1),) * 3 + ((320, 2),) + ((640, 2),) * 2 + ((640, 4),)
+                          + ((1280, 4),) * 2 + ((1280, 8),) * 4) * rows * 2
+            line["nvlink_bytes_per_step_per_unet_rank"] = per_net * 2
+        extra = {}
+        if args.eager_yardstick and world == 1:
+            del loop, unet, nets, mc
+            torch.cuda.empty_cache()
+            try:
+                extra["torch_eager_gpu"] = torch_eager_yardstick(dev, args.latent)
+            except Exception as e:  # noqa: BLE001 - a yardstick must never fail the bench
+                extra["torch_eager_gpu"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        if extra:
+            line["extra"] = extra
+        if args.cpu_baseline and world == 1:
+            step, desc, kind = cpu_reference_step_factory(args.cpu_frames, args.latent)
             t0 = time.perf_counter()
             step()
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": args.cpu_frames / (DDIM_STEPS * dt), "unit": "frames/s", "cores": torch.get_num_threads(),
-                                    "kind": "port", "sample": desc, "ms_per_step": dt * 1e3}
+                                    "kind": kind, "sample": desc, "ms_per_step": dt * 1e3}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -353,7 +478,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--latent", type=int, default=LATENT)
-    ap.add_argument("--cpu-frames", type=int, default=1, help="frames of the bounded CPU sample")
+    ap.add_argument("--cpu-frames", type=int, default=4, help="frames of the bounded CPU sample (>= 4: temporal attention is real)")
+    ap.add_argument("--parallelism", default="windows", choices=["windows", "cfg", "controlnet", "cfg+controlnet"],
+                    help="how N > 1 GPUs are used (see the module docstring)")
+    ap.add_argument("--no-eager-yardstick", dest="eager_yardstick", action="store_false",
+                    help="skip the torch bf16 eager yardstick (the reference's op sequence under stock PyTorch on the same GPU)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--torch-profile", default="", help="write a torch.profiler op table of one eager step to this path")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")

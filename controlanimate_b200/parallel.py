@@ -3,9 +3,13 @@ NVLink 5 / NVSwitch on the B200 box; gloo in the CPU tests).  The path shards on
 
 * frame windows with latent overlap  -> `WindowParallel`  (per-step send/recv of the overlap frames + linear blend)
 * CFG cond / uncond halves           -> `CFGParallel`     (all-gather of the [1,4,f,h,w] noise prediction)
-* the ControlNets of a Multi-ControlNet set -> `ControlNetParallel` (each rank runs its nets; the residual sets are
-  reduced into the UNet rank's skips — by kernel (3) reading the peers' buffers through symmetric memory when
-  available, else after an all-gather)
+* the ControlNets of a Multi-ControlNet set -> `ControlNetParallel` (gloo / fallback transport: the raw residual sets are
+  all-gathered) and `StepParallel` + `SymmetricResiduals` (NVLink transport: the ControlNet ranks' zero-convs write their
+  RAW residuals into symmetric memory and kernel (3) on the UNet rank reads the peers' buffers directly — scale, sum over
+  nets and skip add in ONE pass over NVLink, ordered by device-side signals, no copy and no host synchronisation)
+
+`StepParallel` composes the CFG split with the ControlNet sharding for ONE window (strong scaling: step latency), and
+`WindowParallel` stacks windows on top (weak scaling: frames/s).
 
 Everything else is replicated.  The reference has no distributed code; its only long-video mechanism is the
 SEQUENTIAL sliding window of scripts/vid2vid.py:168-231 (pixel-space hand-off + cross-fade :225-226), which
@@ -129,3 +133,134 @@ class ControlNetParallel:
                         off += t.numel()
                     out[k] = parts
         return out  # type: ignore[return-value]
+
+
+# --------------------------------------------------------------------------------------------------
+# One window over several GPUs: CFG halves x (UNet rank + ControlNet ranks)
+# --------------------------------------------------------------------------------------------------
+class StepParallel:
+    """Rank layout of one denoising step.
+
+    mode "cfg"            : world = 2.  Rank r evaluates CFG row r (ControlNets + UNet at b = 1).
+    mode "controlnet"     : world = G.  Rank 0 runs the UNet (both CFG rows), ranks 1..G-1 the ControlNets.
+    mode "cfg+controlnet" : world = 2 G.  CFG half h = rank // G; inside a half, role 0 runs the UNet, roles 1..G-1 the
+                            ControlNets (net k on role 1 + k % (G - 1)).
+    The UNet rank starts its down path immediately; the ControlNet ranks' residuals are only needed at the skip add
+    (unet.py:567-585), so their 2 x 4.6 TFLOP overlap the UNet's first ~7 TFLOP instead of preceding all 17.8.
+    """
+
+    MODES = ("cfg", "controlnet", "cfg+controlnet")
+
+    def __init__(self, mode: str, rank: int, world: int, n_nets: int, group=None):
+        if mode not in self.MODES:
+            raise ValueError(f"unknown step parallelism {mode!r}")
+        self.mode, self.rank, self.world, self.n_nets, self.group = mode, rank, world, n_nets, group
+        if mode == "cfg":
+            if world != 2:
+                raise ValueError("CFG parallelism is 2-way")
+            self.halves, self.g = 2, 1
+        elif mode == "controlnet":
+            self.halves, self.g = 1, world
+        else:
+            if world % 2:
+                raise ValueError("cfg+controlnet needs an even number of ranks")
+            self.halves, self.g = 2, world // 2
+        if self.g > 1 and (self.g - 1 > n_nets or n_nets < 1):
+            raise ValueError(f"{self.g - 1} ControlNet ranks per CFG half for {n_nets} nets: a rank without a net has nothing to do")
+        self.half = rank // self.g           # which CFG row(s) this rank works on
+        self.role = rank % self.g            # 0 = UNet rank of the half
+
+    @property
+    def is_unet_rank(self) -> bool:
+        return self.role == 0
+
+    @property
+    def unet_rank(self) -> int:
+        """Global rank of the UNet rank of my CFG half."""
+        return self.half * self.g
+
+    def unet_ranks(self) -> List[int]:
+        return [h * self.g for h in range(self.halves)]
+
+    def rows(self, t: torch.Tensor) -> torch.Tensor:
+        """CFG rows of a [2, ...] tensor this rank's half evaluates (both rows when CFG is not split)."""
+        return t[self.half:self.half + 1] if self.halves == 2 else t
+
+    def nets_of(self, role: int) -> List[int]:
+        if self.g == 1:
+            return list(range(self.n_nets)) if role == 0 else []
+        if role == 0:
+            return []
+        return [k for k in range(self.n_nets) if k % (self.g - 1) == role - 1]
+
+    def my_nets(self) -> List[int]:
+        return self.nets_of(self.role)
+
+    def owner_of(self, net: int) -> int:
+        """Global rank (inside my CFG half) that evaluates ControlNet `net`."""
+        if self.g == 1:
+            return self.unet_rank
+        return self.unet_rank + 1 + net % (self.g - 1)
+
+    def combine_noise(self, noise_local: Optional[torch.Tensor], like: torch.Tensor, guidance_scale: float) -> torch.Tensor:
+        """All ranks obtain the guided noise prediction (controlanimation_pipeline.py:845-846): the UNet ranks contribute
+        their rows ([1, 4, f, h, w] each: cfg2 524 KB), the ControlNet ranks a dummy of the same shape."""
+        if noise_local is not None:
+            mine = noise_local.contiguous()
+        else:
+            mine = torch.zeros((1 if self.halves == 2 else 2, *like.shape[1:]), dtype=like.dtype, device=like.device)
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(parts, mine, group=self.group)
+        rows = [parts[r] for r in self.unet_ranks()]
+        if self.halves == 2:
+            return rows[0] + guidance_scale * (rows[1] - rows[0])
+        u, c = rows[0].chunk(2)
+        return u + guidance_scale * (c - u)
+
+
+class SymmetricResiduals:
+    """The NVLink transport of the ControlNet sharding: one symmetric-memory arena per rank holding the RAW residuals of the
+    nets that rank evaluates ([(b f), c_i, h_i, w_i] channels_last, 13 per net, back to back).  Owners write through
+    `out_views(slot)` (the zero-conv GEMMs store straight into the arena); the UNet rank reads `peer_views(rank, slot)` —
+    tensors that alias the PEER's memory, handed to kernel (3) like local ones (`ld.global` over NVLink).  Ordering is by
+    device-side signals on the current stream: `publish()` / `wait_published()` before the merge, `release()` /
+    `wait_released()` before the owners overwrite the arena in the next step."""
+
+    def __init__(self, shapes: Sequence[Tuple[int, int, int, int]], slots: int, dtype, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.shapes = [tuple(int(v) for v in s) for s in shapes]              # (n, c, h, w) of the 13 residuals of one net
+        self.per_net = sum(n * c * h * w for n, c, h, w in self.shapes)
+        self.slots, self.dtype, self.device = slots, dtype, device
+        group = group if group is not None else dist.group.WORLD
+        self.arena = symm_mem.empty(max(1, slots) * self.per_net, dtype=dtype, device=device)
+        self.handle = symm_mem.rendezvous(self.arena, group)
+        self.rank = self.handle.rank
+
+    def _views(self, flat: torch.Tensor, slot: int) -> List[torch.Tensor]:
+        out, off = [], slot * self.per_net
+        for n, c, h, w in self.shapes:
+            out.append(flat[off:off + n * c * h * w].view(n, h, w, c).permute(0, 3, 1, 2))   # channels_last [(b f), c, h, w]
+            off += n * c * h * w
+        return out
+
+    def out_views(self, slot: int) -> List[torch.Tensor]:
+        return self._views(self.arena, slot)
+
+    def peer_views(self, rank: int, slot: int) -> List[torch.Tensor]:
+        if rank == self.rank:
+            return self.out_views(slot)
+        flat = self.handle.get_buffer(rank, (self.arena.numel(),), self.dtype, 0)
+        return self._views(flat, slot)
+
+    # device-side ordering (stream-ordered signal kernels on the symmetric signal pads; no host synchronisation)
+    def publish(self, to_rank: int):
+        self.handle.put_signal(to_rank, channel=0)
+
+    def wait_published(self, from_rank: int):
+        self.handle.wait_signal(from_rank, channel=0)
+
+    def release(self, to_rank: int):
+        self.handle.put_signal(to_rank, channel=1)
+
+    def wait_released(self, from_rank: int):
+        self.handle.wait_signal(from_rank, channel=1)

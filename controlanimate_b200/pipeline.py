@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import torch
 
-from .residuals import ResidualSet, merge_controlnet_residuals
+from .residuals import RemoteResidualSet, ResidualSet, merge_controlnet_residuals
 from .unet import ControlNetModel, UNet3DConditionModel
 
 
@@ -63,15 +63,22 @@ class MultiControlNetResiduals:
         self.prep_images: Optional[List[torch.Tensor]] = None
         self.lazy = True  # hand the UNet a ResidualSet (single-pass merge) instead of merged tensors
 
-    def raw(self, control_model_input, t, controlnet_prompt_embeds, frame_count, nets=None):
+    def raw(self, control_model_input, t, controlnet_prompt_embeds, frame_count, nets=None, images=None, out=None,
+            sample_offset: int = 0):
+        """Raw residual lists of the nets in `nets` (default: all).  `images[k]` overrides prep_images[k] (a CFG half's
+        rows), `out[j]` gives the 13 output buffers of the j-th evaluated net (symmetric memory of a sharded set),
+        `sample_offset` the index of this call's first sample in the full (b f) batch (a CFG half evaluates rows
+        [half * f, (half + 1) * f) and must see the prompts the reference's tiling quirk gives exactly those rows)."""
         b = control_model_input.shape[0]
         x = control_model_input.permute(0, 2, 1, 3, 4).reshape(b * frame_count, *control_model_input.shape[1:2],
                                                                *control_model_input.shape[3:])   # :287
         # :292 tiles the prompt embeddings as cat([e]*f): row n of the tiled tensor is e[n % b] (kept as-is, see SURVEY §8a quirks)
         n_prompts = controlnet_prompt_embeds.shape[0]
-        ctx_map = torch.arange(b * frame_count, device=x.device) % n_prompts
-        nets = range(len(self.controlnets)) if nets is None else nets
-        return [self.controlnets[k](x, t, controlnet_prompt_embeds, self.prep_images[k], ctx_map=ctx_map) for k in nets]
+        ctx_map = (sample_offset + torch.arange(b * frame_count, device=x.device)) % n_prompts
+        nets = list(range(len(self.controlnets))) if nets is None else list(nets)
+        images = self.prep_images if images is None else images
+        return [self.controlnets[k](x, t, controlnet_prompt_embeds, images[k], ctx_map=ctx_map,
+                                    out=None if out is None else out[j]) for j, k in enumerate(nets)]
 
     def __call__(self, control_model_input, t, controlnet_prompt_embeds, frame_count, image_embeds=None,
                  do_classifier_free_guidance=True, guess_mode=True):
@@ -91,11 +98,20 @@ class DenoisingLoop:
     """
 
     def __init__(self, unet: UNet3DConditionModel, controlnets: Optional[MultiControlNetResiduals], scheduler: DDIMScheduler,
-                 guidance_scale: float = 7.5, guess_mode: bool = False, use_cuda_graph: bool = False):
+                 guidance_scale: float = 7.5, guess_mode: bool = False, use_cuda_graph: bool = False, parallel=None):
+        """parallel: a `parallel.StepParallel` — this window's step is split over its ranks (CFG halves and / or ControlNet
+        sharding over NVLink); every rank of the group must call `step` with the same latents."""
         self.unet, self.controlnets, self.scheduler = unet, controlnets, scheduler
         self.guidance_scale, self.guess_mode = guidance_scale, guess_mode
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
+        self.parallel = parallel
+        self._transport = None
+        if parallel is not None:
+            if guess_mode or guidance_scale <= 1.0:
+                raise ValueError("step parallelism covers the CFG path without guess mode (BASELINE configs 2-4)")
+            if parallel.g > 1 and controlnets is None:
+                raise ValueError("ControlNet sharding needs a ControlNet set")
 
     @property
     def do_cfg(self):
@@ -103,6 +119,9 @@ class DenoisingLoop:
 
     def predict_noise(self, latents: torch.Tensor, t, prompt_embeds: torch.Tensor) -> torch.Tensor:
         """Guided noise prediction for latents [1,4,f,h,w]; `t` is an int or a 1-element int64 device tensor."""
+        if self.parallel is not None:
+            local = self._local_noise(latents, t, prompt_embeds)
+            return self.parallel.combine_noise(local, latents, self.guidance_scale)
         f = latents.shape[2]
         cfg = self.do_cfg
         model_in = torch.cat([latents] * 2) if cfg else latents                                          # :797
@@ -132,6 +151,67 @@ class DenoisingLoop:
             self._params = [p for m in mods for p in list(m.parameters()) + list(m.buffers())]
         return hash(tuple(p.data_ptr() for p in self._params)), sum(p._version for p in self._params)
 
+    # ---- one window over several GPUs (parallel.StepParallel) --------------------------------------------------------
+    def _transport_for(self, latents: torch.Tensor):
+        """Symmetric-memory arena for the sharded ControlNets' raw residuals, created (collectively) on first use."""
+        sp = self.parallel
+        if sp.g == 1:
+            return None
+        if self._transport is None:
+            from .parallel import SymmetricResiduals
+            from .residuals import N_RESIDUALS  # noqa: F401
+            f, hh, ww = latents.shape[2], latents.shape[3], latents.shape[4]
+            rows = (1 if sp.halves == 2 else 2) * f
+            cn = self.controlnets.controlnets[0]
+            boc, lpb = cn.config["block_out_channels"], cn.config["layers_per_block"]
+            shapes, h, w = [(rows, boc[0], hh, ww)], hh, ww
+            for i, c in enumerate(boc):
+                shapes += [(rows, c, h, w)] * lpb
+                if i != len(boc) - 1:
+                    h, w = (h + 1) // 2, (w + 1) // 2
+                    shapes.append((rows, c, h, w))
+            shapes.append((rows, boc[-1], h, w))
+            slots = max(len(sp.nets_of(r)) for r in range(sp.g))
+            self._transport = SymmetricResiduals(shapes, slots, self.unet.conv_in.weight.dtype, latents.device, sp.group)
+            if sp.is_unet_rank:      # the arenas start out free: the owners' first wait_released must not block
+                for o in sorted({sp.owner_of(k) for k in range(sp.n_nets)}):
+                    self._transport.release(o)
+        return self._transport
+
+    def _local_noise(self, latents: torch.Tensor, t, prompt_embeds: torch.Tensor) -> Optional[torch.Tensor]:
+        """This rank's share of one noise prediction (no collective inside: capturable in a CUDA graph).  UNet ranks
+        return their CFG row(s) of the UNet output, ControlNet ranks publish their residuals and return None."""
+        sp, mc = self.parallel, self.controlnets
+        f = latents.shape[2]
+        model_in = latents if sp.halves == 2 else torch.cat([latents] * 2)
+        prompt = sp.rows(prompt_embeds)
+        # the ControlNets always see BOTH prompts: row n of the (b f) batch takes prompt n % 2 (the tiling quirk of
+        # controlresiduals_pipeline.py:292 is part of the reference's arithmetic), n counted over the full CFG batch
+        offset = sp.half * f if sp.halves == 2 else 0
+        images = None
+        if mc is not None:
+            images = [im[sp.half * f:(sp.half + 1) * f] if sp.halves == 2 else im for im in mc.prep_images]
+        tr = self._transport_for(latents)
+        if not sp.is_unet_rank:                                   # ControlNet rank: evaluate, store into the arena, publish
+            nets = sp.my_nets()
+            tr.wait_released(sp.unet_rank)
+            mc.raw(model_in, t, prompt_embeds, f, nets=nets, images=images, out=[tr.out_views(j) for j in range(len(nets))],
+                   sample_offset=offset)
+            tr.publish(sp.unet_rank)
+            return None
+        down = None
+        if mc is not None and sp.g == 1:                          # CFG split only: my row's ControlNets run here
+            down = ResidualSet(mc.raw(model_in, t, prompt_embeds, f, images=images, sample_offset=offset), mc.cond_scale, f, False)
+        elif mc is not None:                                      # sharded: kernel (3) will read the owners' arenas over NVLink
+            per_net, owners = [], []
+            for k in range(sp.n_nets):
+                owner = sp.owner_of(k)
+                slot = sp.nets_of(owner - sp.unet_rank).index(k)
+                per_net.append(tr.peer_views(owner, slot))
+                owners.append(owner)
+            down = RemoteResidualSet(per_net, mc.cond_scale, f, False, tr, owners)
+        return self.unet(model_in, t, encoder_hidden_states=prompt, down_block_additional_residuals=down).sample.to(latents.dtype)
+
     def _graphed_noise(self, latents, t: int, prompt_embeds):
         mc = self.controlnets
         images = list(mc.prep_images) if mc is not None and mc.prep_images is not None else []
@@ -153,13 +233,15 @@ class DenoisingLoop:
             try:
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
+                # with step parallelism only this rank's share is captured; the (tiny) all-gather + CFG combine stay eager
+                fn = self.predict_noise if self.parallel is None else self._local_noise
                 with torch.cuda.stream(side):                # warm-up: cuDNN algorithm selection, caches, workspaces
                     for _ in range(2):
-                        self.predict_noise(s_lat, s_t, s_prompt)
+                        fn(s_lat, s_t, s_prompt)
                 torch.cuda.current_stream().wait_stream(side)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    s_out = self.predict_noise(s_lat, s_t, s_prompt)
+                    s_out = fn(s_lat, s_t, s_prompt)
             finally:
                 if mc is not None:
                     mc.prep_images = images if images else None
@@ -175,6 +257,8 @@ class DenoisingLoop:
                 g["seen"][k] = ident
         g["t"].fill_(int(t))
         g["graph"].replay()
+        if self.parallel is not None:
+            return self.parallel.combine_noise(g["out"], latents, self.guidance_scale)
         return g["out"]
 
     @torch.no_grad()

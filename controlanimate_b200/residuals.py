@@ -81,6 +81,29 @@ class ResidualSet:
         return list(down), mid
 
 
+class RemoteResidualSet(ResidualSet):
+    """A ResidualSet whose per-net tensors alias OTHER ranks' symmetric memory (parallel.SymmetricResiduals): kernel (3)
+    reads them over NVLink while it scales, sums and adds into the local skips — the ControlNet "reduce" of SURVEY §8e
+    fused into the consumer.  The first add waits (on the stream, device side) until every owner has published its
+    residuals; after the last read of the step (the mid-block add, unet.py:584-585) the owners are released."""
+
+    def __init__(self, per_net, cond_scale, frames, guess_mode, transport, owners: Sequence[int]):
+        super().__init__(per_net, cond_scale, frames, guess_mode)
+        self.transport = transport
+        self.owners = sorted({int(o) for o in owners if int(o) != transport.rank})
+        self._waited = False
+
+    def add_into(self, skips, mid):
+        if not self._waited:
+            for o in self.owners:
+                self.transport.wait_published(o)
+            self._waited = True
+        super().add_into(skips, mid)
+        if mid is not None:
+            for o in self.owners:
+                self.transport.release(o)
+
+
 class _MergedResiduals(ResidualSet):
     """Already-merged tensors in the reference layout [b, c, f, h, w] (the plain B3 contract)."""
 

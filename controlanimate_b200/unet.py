@@ -324,12 +324,17 @@ class ControlNetModel(nn.Module):
         self._temb_bank = Ly.TembBank()
 
     @staticmethod
-    def _zero_conv(conv: nn.Conv2d, x4: torch.Tensor) -> torch.Tensor:
+    def _zero_conv(conv: nn.Conv2d, x4: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         n, c, h, w = x4.shape
-        y = ops.linear(Ly.tokens(Ly._cl(x4)), conv.weight.reshape(c, c), Ly.f32(conv.bias))   # 1x1 conv == token GEMM
+        if out is not None:   # store straight into the caller's buffer (e.g. a symmetric-memory arena read by a peer GPU)
+            if tuple(out.shape) != (n, c, h, w) or not out.permute(0, 2, 3, 1).is_contiguous() or out.dtype != x4.dtype:
+                raise ValueError("ControlNet output buffers must be channels_last tensors of the residual shapes")
+            out = Ly.tokens(out)
+        y = ops.linear(Ly.tokens(Ly._cl(x4)), conv.weight.reshape(c, c), Ly.f32(conv.bias), out=out)   # 1x1 conv == token GEMM
         return Ly.from_tokens(y, n, h, w)
 
-    def forward(self, sample, timestep, encoder_hidden_states, controlnet_cond, ctx_map=None) -> List[torch.Tensor]:
+    def forward(self, sample, timestep, encoder_hidden_states, controlnet_cond, ctx_map=None,
+                out: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
         dtype = self.conv_in.weight.dtype
         n = sample.shape[0]
         if not torch.is_tensor(timestep):
@@ -361,6 +366,7 @@ class ControlNetModel(nn.Module):
         x = mb.resnets[0].native(x, emb, frames, next(shifts))
         x = mb.attentions[0].native(x, frames, ctx, ctx_map)
         x = mb.resnets[1].native(x, emb, frames, next(shifts))
-        out = [self._zero_conv(z, s) for z, s in zip(self.controlnet_down_blocks, skips)]
-        out.append(self._zero_conv(self.controlnet_mid_block, x))
-        return out
+        bufs = list(out) if out is not None else [None] * (len(skips) + 1)
+        res = [self._zero_conv(z, s, o) for z, s, o in zip(self.controlnet_down_blocks, skips, bufs)]
+        res.append(self._zero_conv(self.controlnet_mid_block, x, bufs[-1]))
+        return res

@@ -7,6 +7,27 @@ import torch
 import torch.nn as nn
 
 
+# Architecture of the headline workload: SD1.5 UNet3D + mm_sd_v15_v2 motion modules (reference
+# configs/inference/inference-v2.yaml:1-22 on top of the SD1.5 UNet config).
+MOTION_MODULE_KWARGS_V2 = dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=("Temporal_Self", "Temporal_Self"),
+                               temporal_position_encoding=True, temporal_position_encoding_max_len=32, temporal_attention_dim_div=1)
+
+
+def sd15_unet3d_config(time_cond_proj_dim=None) -> dict:
+    """Ctor kwargs of `UNet3DConditionModel` for SD1.5 + v2 motion modules (time_cond_proj_dim=256 for LCM checkpoints)."""
+    cfg = dict(sample_size=64, in_channels=4, out_channels=4,
+               down_block_types=("CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "DownBlock3D"),
+               up_block_types=("UpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D"),
+               block_out_channels=(320, 640, 1280, 1280), layers_per_block=2, cross_attention_dim=768, attention_head_dim=8,
+               norm_num_groups=32, norm_eps=1e-5, use_inflated_groupnorm=True, unet_use_cross_frame_attention=False,
+               unet_use_temporal_attention=False, use_motion_module=True, motion_module_resolutions=(1, 2, 4, 8),
+               motion_module_mid_block=True, motion_module_decoder_only=False, motion_module_type="Vanilla",
+               motion_module_kwargs=dict(MOTION_MODULE_KWARGS_V2))
+    if time_cond_proj_dim:
+        cfg["time_cond_proj_dim"] = time_cond_proj_dim
+    return cfg
+
+
 def analytic_pe(max_len: int, dim: int, device=None) -> torch.Tensor:
     """PositionalEncoding buffer, reference motion_module.py:236-244."""
     position = torch.arange(max_len, device=device).unsqueeze(1)

@@ -84,3 +84,46 @@ def test_controlnet_parallel_gather():
 
 def test_window_starts_match_config3():
     assert P.window_starts(5, 16, 4) == [0, 12, 24, 36, 48]
+
+
+def test_step_parallel_role_tables():
+    """Rank layouts of parallel.StepParallel (no process group needed)."""
+    sp = [P.StepParallel("cfg+controlnet", r, 4, n_nets=2) for r in range(4)]
+    assert [s.half for s in sp] == [0, 0, 1, 1] and [s.role for s in sp] == [0, 1, 0, 1]
+    assert sp[0].my_nets() == [] and sp[1].my_nets() == [0, 1] and sp[3].my_nets() == [0, 1]
+    assert sp[2].unet_rank == 2 and sp[3].unet_rank == 2 and sp[0].unet_ranks() == [0, 2]
+    assert [sp[2].owner_of(k) for k in range(2)] == [3, 3]
+    sp6 = [P.StepParallel("cfg+controlnet", r, 6, n_nets=2) for r in range(6)]
+    assert [s.my_nets() for s in sp6] == [[], [0], [1], [], [0], [1]]
+    assert [sp6[3].owner_of(k) for k in range(2)] == [4, 5]
+    cfg = [P.StepParallel("cfg", r, 2, n_nets=2) for r in range(2)]
+    assert cfg[0].my_nets() == [0, 1] and cfg[1].is_unet_rank and cfg[1].half == 1
+    cn = [P.StepParallel("controlnet", r, 3, n_nets=4) for r in range(3)]
+    assert [s.my_nets() for s in cn] == [[], [0, 2], [1, 3]] and all(s.half == 0 for s in cn)
+    with pytest.raises(ValueError):
+        P.StepParallel("cfg", 0, 3, n_nets=2)
+    with pytest.raises(ValueError):
+        P.StepParallel("controlnet", 0, 4, n_nets=2)       # 3 ControlNet ranks for 2 nets
+    with pytest.raises(ValueError):
+        P.ControlNetParallel(0, 3, 2)
+
+
+def _combine_worker(rank, world):
+    g = torch.Generator().manual_seed(13)
+    noise = torch.randn(2, 4, 3, 4, 4, generator=g)
+    u, c = noise.chunk(2)
+    want = u + 7.5 * (c - u)
+    like = torch.zeros(1, 4, 3, 4, 4)
+    if world == 4:      # CFG halves x (UNet rank + ControlNet rank)
+        sp = P.StepParallel("cfg+controlnet", rank, world, n_nets=2)
+        local = sp.rows(noise) if sp.is_unet_rank else None
+    else:               # UNet rank (both rows) + one ControlNet rank
+        sp = P.StepParallel("controlnet", rank, world, n_nets=2)
+        local = noise if sp.is_unet_rank else None
+    out = sp.combine_noise(local, like, 7.5)
+    assert torch.allclose(out, want, atol=1e-6)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_step_parallel_combine_noise(world):
+    _run(_combine_worker, world)
