@@ -19,7 +19,7 @@ from typing import Dict
 
 import torch.nn as nn
 
-from .layers import B200MotionModule, B200ResnetBlock3D, B200TemporalAttnProcessor
+from .layers import B200IPAttnProcessor, B200MotionModule, B200ResnetBlock3D, B200TemporalAttnProcessor
 
 
 def _is_versatile_attention(m: nn.Module) -> bool:
@@ -59,9 +59,45 @@ def _convert_resnet(old: nn.Module) -> B200ResnetBlock3D:
     return new.to(device=p.device, dtype=p.dtype).eval()
 
 
-def install(unet: nn.Module, *, processors: bool = True, motion_modules: bool = True, resnets: bool = True) -> Dict[str, int]:
-    """Mutates `unet` in place; returns how many modules of each kind were replaced."""
-    counts = dict(processors=0, motion_modules=0, resnets=0)
+def _controlnet_call(self, control_model_input, t, controlnet_prompt_embeds, frame_count, image_embeds=None,
+                     do_classifier_free_guidance=True, guess_mode=True):
+    """Replacement for `MultiControlNetResidualsPipeline.__call__` (reference modules/controlresiduals_pipeline.py:278-316).
+    Same inputs; every ControlNet is evaluated with conditioning_scale 1 (RAW residuals) and the scale-and-sum of diffusers'
+    MultiControlNetModel, the 13 rearranges of :304-312 and the UNet's skip adds are left to kernel (3): the return value is
+    a tuple of `LazyResidual` proxies that the UNMODIFIED reference UNet consumes through `skip + residual`."""
+    import torch
+    from .residuals import ResidualSet
+    b, c, f, h, w = control_model_input.shape
+    x = control_model_input.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)                      # :287
+    prompt = torch.cat([controlnet_prompt_embeds] * frame_count)                                # :292 (tiling kept as is)
+    nets = list(getattr(self.controlnet, "nets", [self.controlnet]))
+    dtype = next(nets[0].parameters()).dtype if hasattr(nets[0], "parameters") and any(True for _ in nets[0].parameters()) else x.dtype
+    images = self.prep_images if isinstance(self.prep_images, (list, tuple)) else [self.prep_images]
+    per_net = []
+    for k, net in enumerate(nets):
+        down, mid = net(x.to(dtype), t, encoder_hidden_states=prompt.to(dtype), controlnet_cond=images[k], conditioning_scale=1.0,
+                        guess_mode=False, return_dict=False)                                    # :294-302, unscaled
+        per_net.append(list(down) + [mid])
+    scales = self.cond_scale if isinstance(self.cond_scale, (list, tuple)) else [self.cond_scale] * len(nets)
+    return ResidualSet(per_net, list(scales), frame_count, bool(guess_mode)).lazy_tuple()
+
+
+def install_controlnet_pipeline(pipe) -> None:
+    """Boundary B3 producer side: make `pipe(...)` (a MultiControlNetResidualsPipeline) return lazy residual sets."""
+    cls = type(pipe)
+    if getattr(cls, "_ca_b200", False):
+        return
+    pipe.__class__ = type("B200" + cls.__name__, (cls,), {"__call__": _controlnet_call, "_ca_b200": True})
+
+
+def install(unet: nn.Module, controlnet_pipeline=None, *, processors: bool = True, motion_modules: bool = True,
+            resnets: bool = True) -> Dict[str, int]:
+    """Mutates `unet` (and, when given, `controlnet_pipeline`) in place; returns how many modules of each kind were
+    replaced.  `install(pipe.pipeline.unet, pipe.pipeline.controlnet)` covers boundaries B1-B4."""
+    counts = dict(processors=0, motion_modules=0, resnets=0, controlnet_pipeline=0)
+    if controlnet_pipeline is not None:
+        install_controlnet_pipeline(controlnet_pipeline)
+        counts["controlnet_pipeline"] = 1
     if motion_modules or resnets:
         for parent in list(unet.modules()):
             for name, child in list(parent.named_children()):
@@ -93,3 +129,21 @@ def verify_installed(unet: nn.Module) -> bool:
     """True iff every temporal attention still dispatches to a B200 processor (nothing overwrote them)."""
     mods = [m for m in unet.modules() if _is_versatile_attention(m)]
     return bool(mods) and all(isinstance(m.get_processor(), B200TemporalAttnProcessor) for m in mods)
+
+
+def set_ip_adapter(unet: nn.Module, scale: float = 1.0, num_tokens: int = 4) -> Dict[str, nn.Module]:
+    """Mirror of `IPAdapter.set_ip_adapter` (reference modules/ip_adapter.py:95-126) with B200 processors: every
+    cross-attention (`attn2`) gets a `B200IPAttnProcessor` (dual-KV kernel path), every other attention keeps what it has
+    (the reference installs a plain AttnProcessor2_0 there, which the B200 temporal processor is equivalent to).
+    Returns {attn_processors key: processor} of the installed IP processors, in `attn_processors` order, so that
+    `torch.nn.ModuleList(procs.values())` can be handed to the reference's weight loader (ip_adapter.py:184)."""
+    cross_dim = unet.config["cross_attention_dim"] if isinstance(unet.config, dict) else unet.config.cross_attention_dim
+    procs = {}
+    for name, m in unet.named_modules():
+        if name.endswith("attn2") and hasattr(m, "set_processor"):
+            hidden = m.to_q.weight.shape[0]
+            p = B200IPAttnProcessor(hidden_size=hidden, cross_attention_dim=cross_dim, scale=scale, num_tokens=num_tokens)
+            p = p.to(device=m.to_q.weight.device, dtype=m.to_q.weight.dtype)
+            m.set_processor(p)
+            procs[f"{name}.processor"] = p
+    return procs

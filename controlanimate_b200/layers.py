@@ -48,10 +48,20 @@ def f32(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 
 def to_native(x: torch.Tensor) -> torch.Tensor:
-    """[b,c,f,h,w] (any dense layout) -> same logical tensor with BFHWC memory order (copy only if needed)."""
-    if ops.video_layout(x) == L.CA_LAYOUT_BFHWC:
-        return x
-    return x.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
+    """[b,c,f,h,w] with ANY strides -> same logical tensor with BFHWC memory order (copy only if needed).  The reference
+    hands its modules whatever `rearrange` produced, e.g. the "(b f) c h w -> b c f h w" VIEW behind every InflatedConv3d
+    (resnet.py:16-18), which is neither NCFHW-contiguous nor BFHWC."""
+    if x.dim() != 5:
+        raise ValueError(f"expected a 5-D [b,c,f,h,w] tensor, got {tuple(x.shape)}")
+    p = x.permute(0, 2, 3, 4, 1)
+    return x if p.is_contiguous() else p.contiguous().permute(0, 4, 1, 2, 3)
+
+
+def _like_input(y5: torch.Tensor, x5: torch.Tensor) -> torch.Tensor:
+    """Drop-in modules return NCFHW-contiguous tensors for NCFHW-contiguous inputs (what a caller that allocated such a tensor
+    may rely on) and the native BFHWC layout otherwise: every consumer in the reference is a strided torch op / rearrange,
+    and `b c f h w -> (b f) c h w` of a BFHWC tensor is a free channels_last view (no copy in front of the next cuDNN conv)."""
+    return y5.contiguous() if x5.is_contiguous() else y5
 
 
 def frames4(x5: torch.Tensor) -> torch.Tensor:
@@ -276,7 +286,16 @@ class TemporalAttention(nn.Module):
         self.processor = B200TemporalAttnProcessor()
         self._qkv = _FusedWeights()
 
+    # processors that are plain softmax(q k^T) v self-attention: arithmetically what B200TemporalAttnProcessor computes
+    _PLAIN = ("AttnProcessor", "AttnProcessor2_0", "XFormersAttnProcessor")
+
     def set_processor(self, processor, _remove_lora=False):
+        """`set_ip_adapter` (modules/ip_adapter.py:95-126) and `enable_xformers_memory_efficient_attention`
+        (controlanimate_pipeline.py:112) overwrite EVERY processor of the UNet, the temporal ones with a plain
+        AttnProcessor2_0 / xformers processor.  Those compute exactly what the B200 processor computes, so the B200
+        processor survives; any other (foreign) processor is honoured through the AttentionProcessor protocol."""
+        if type(processor).__name__ in self._PLAIN and isinstance(getattr(self, "processor", None), B200TemporalAttnProcessor):
+            return
         if isinstance(getattr(self, "processor", None), nn.Module) and not isinstance(processor, nn.Module):
             self._modules.pop("processor", None)
         self.processor = processor
@@ -385,10 +404,9 @@ class B200MotionModule(nn.Module):
     def forward(self, input_tensor, temb=None, encoder_hidden_states=None, attention_mask=None, anchor_frame_idx=None):
         if input_tensor.dim() != 5:
             raise ValueError(f"Expected hidden_states to have ndim=5, but got ndim={input_tensor.dim()}.")
-        native_in = ops.video_layout(input_tensor) == L.CA_LAYOUT_BFHWC
         x5 = to_native(input_tensor)
         y5 = video5(self.native(frames4(x5), x5.shape[2]), x5.shape[2])
-        return y5 if native_in else y5.contiguous()
+        return _like_input(y5, input_tensor)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -452,10 +470,9 @@ class B200ResnetBlock3D(nn.Module):
         return ops.bias_act_residual(h, f32(self.conv2.bias), x4, scale=inv, inplace=True)
 
     def forward(self, input_tensor, temb):
-        native_in = ops.video_layout(input_tensor) == L.CA_LAYOUT_BFHWC
         x5 = to_native(input_tensor)
         y5 = video5(self.native(frames4(x5), temb, x5.shape[2]), x5.shape[2])
-        return y5 if native_in else y5.contiguous()
+        return _like_input(y5, input_tensor)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -479,6 +496,55 @@ def _ctx_i32(ctx_map: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return hit[1]
 
 
+class B200IPAttnProcessor(nn.Module):
+    """IP-Adapter dual-KV cross-attention (reference modules/attention_processor.py:367-492, `IPAttnProcessor2_0`): the
+    last `num_tokens` rows of encoder_hidden_states are image tokens with their own K/V projections,
+        out = to_out( softmax(q k_text^T) v_text + scale * softmax(q k_ip^T) v_ip ).
+    Same ctor arguments and parameter names (`to_k_ip.weight`, `to_v_ip.weight`) as the reference class, so the loader of
+    modules/ip_adapter.py:136-185 fills it; both softmaxes run on the cross-attention kernel (K/V resident in smem).
+    Works as a drop-in AttentionProcessor (`__call__` protocol) and is recognised by the native spatial transformer."""
+
+    def __init__(self, hidden_size, cross_attention_dim=None, scale=1.0, num_tokens=4):
+        super().__init__()
+        self.hidden_size, self.cross_attention_dim, self.scale, self.num_tokens = hidden_size, cross_attention_dim, scale, num_tokens
+        self.to_k_ip = nn.Linear(cross_attention_dim or hidden_size, hidden_size, bias=False)
+        self.to_v_ip = nn.Linear(cross_attention_dim or hidden_size, hidden_size, bias=False)
+        self._kv = _FusedWeights()
+        self._kv_ip = _FusedWeights()
+
+    @staticmethod
+    def attend(proc, attn, q_tok, ctx, n_frames, d, ctx_map=None):
+        """q_tok [(n_frames d), C] token-major, ctx [B_ctx, L, D] -> attention output [(n_frames d), C] before to_out.
+        `proc` is any module with to_k_ip / to_v_ip / scale / num_tokens (this class or the reference's)."""
+        c = q_tok.shape[-1]
+        end = ctx.shape[1] - int(proc.num_tokens)
+        if end <= 0:
+            raise ValueError("encoder_hidden_states holds no text tokens in front of the image tokens")
+        fuse = getattr(proc, "_kv", None) or _FusedWeights()
+        fuse_ip = getattr(proc, "_kv_ip", None) or _FusedWeights()
+        kv = ops.linear(ctx[:, :end].contiguous(), fuse.get(attn.to_k.weight, attn.to_v.weight))
+        kv_ip = ops.linear(ctx[:, end:].contiguous(), fuse_ip.get(proc.to_k_ip.weight, proc.to_v_ip.weight))
+        cmap = _ctx_i32(ctx_map)
+        o = ops.cross_attention_core(q_tok, kv[:, :, :c], kv[:, :, c:], frames=n_frames, sites=d, heads=attn.heads,
+                                     ctx_of_frame=cmap, scale=attn.scale)
+        o_ip = ops.cross_attention_core(q_tok, kv_ip[:, :, :c], kv_ip[:, :, c:], frames=n_frames, sites=d, heads=attn.heads,
+                                        ctx_of_frame=cmap, scale=attn.scale)
+        return o.add_(o_ip, alpha=float(proc.scale))
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
+        if attention_mask is not None or encoder_hidden_states is None or hidden_states.dim() != 3:
+            raise ValueError("B200IPAttnProcessor handles cross-attention on [(b f), d, C] tokens without a mask")
+        for name in ("spatial_norm", "group_norm", "norm_cross"):
+            if getattr(attn, name, None) is not None:
+                raise ValueError(f"attn.{name} is not supported")
+        n, d, c = hidden_states.shape
+        x = hidden_states.contiguous().reshape(n * d, c)
+        q_tok = ops.linear(x, attn.to_q.weight)
+        o = self.attend(self, attn, q_tok, encoder_hidden_states.to(x.dtype), n, d)
+        out = ops.linear(o, attn.to_out[0].weight, f32(attn.to_out[0].bias))
+        return out.reshape(n, d, c)
+
+
 class _SpatialAttention(nn.Module):
     def __init__(self, dim, heads, cross_dim=None):
         super().__init__()
@@ -494,6 +560,8 @@ class _SpatialAttention(nn.Module):
         self._fused = _FusedWeights()
 
     def set_processor(self, processor, _remove_lora=False):
+        if isinstance(getattr(self, "processor", None), nn.Module) and not isinstance(processor, nn.Module):
+            self._modules.pop("processor", None)
         self.processor = processor
 
     def get_processor(self, return_deprecated_lora: bool = False):
@@ -508,6 +576,9 @@ class _SpatialAttention(nn.Module):
             q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))
         else:
             q_tok = ops.linear(n_tok, self.to_q.weight)                                      # [T, C] token-major
+            if hasattr(self.processor, "to_k_ip"):                                           # IP-Adapter dual-KV (config 4)
+                o = B200IPAttnProcessor.attend(self.processor, self, q_tok, ctx, n_frames, d, ctx_map)
+                return ops.linear(o, self.to_out[0].weight, f32(self.to_out[0].bias), residual=residual)
             kv = ops.linear(ctx, self._fused.get(self.to_k.weight, self.to_v.weight))        # [B_ctx, L, 2C], once per prompt
             if hd in (40, 80, 160) and kv.shape[1] <= 96 and (ctx_map is not None or n_frames % kv.shape[0] == 0):
                 # own kernel (row N2): K/V of a (prompt, head) stay in smem, Q streams in and O out once

@@ -73,12 +73,51 @@ class ResidualSet:
             ops.residual_merge([r[-1:] for r in self.per_net], [s[-1:] for s in self.scales], [mid],
                                frames=self.frames, add_into_dst=True, layout=self.layout)
 
+    def added_to(self, skip: torch.Tensor, index: int) -> torch.Tensor:
+        """`skip + Σ_k s_k r_{k,index}` as a NEW tensor in the skip's layout: what the reference's UNet computes at
+        unet.py:572 / :585 when it adds entry `index` of the residual tuple (the B3 drop-in route: see LazyResidual)."""
+        if skip.is_contiguous() or skip.permute(0, 2, 3, 4, 1).is_contiguous():
+            out = skip.clone(memory_format=torch.preserve_format)
+        else:                                   # a rearrange view of the reference: densify in the native layout
+            out = skip.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
+        layout = ops.video_layout(out)
+        srcs = [[r[index]] for r in self.per_net]
+        want_cl = layout == L.CA_LAYOUT_BFHWC
+        srcs = [[t if t.is_contiguous(memory_format=torch.channels_last) == want_cl and (want_cl or t.is_contiguous())
+                 else t.contiguous(memory_format=torch.channels_last if want_cl else torch.contiguous_format) for t in row] for row in srcs]
+        ops.residual_merge(srcs, [[s[index]] for s in self.scales], [out], frames=self.frames, add_into_dst=True, layout=layout)
+        return out
+
+    def lazy_tuple(self):
+        """(down_block_additional_residuals, mid_block_additional_residual) as LazyResidual proxies."""
+        n = self.n_res
+        return tuple(LazyResidual(self, i) for i in range(n - 1)), LazyResidual(self, n - 1)
+
     def materialize(self) -> Tuple[Tuple[torch.Tensor, ...], torch.Tensor]:
         return merge_controlnet_residuals(self.per_net, None, self.frames, scales=self.scales)
 
     def _materialize_lists(self):
         down, mid = self.materialize()
         return list(down), mid
+
+
+class LazyResidual:
+    """One entry of `down_block_additional_residuals` (or the mid residual) that is still a per-net RAW set.  The
+    reference's UNet adds residuals with `skip + residual` (animatediff/models/unet.py:572, :585); for an operand torch does
+    not know, Python falls back to `residual.__radd__(skip)`, which runs kernel (3): per-net scales, sum over the nets,
+    the '(b f) c h w -> b c f h w' rearrange and the skip add in one pass — without touching the reference's forward."""
+
+    def __init__(self, rset: "ResidualSet", index: int):
+        self.rset, self.index = rset, index
+
+    def __radd__(self, skip: torch.Tensor) -> torch.Tensor:
+        return self.rset.added_to(skip, self.index)
+
+    __add__ = __radd__
+
+    def materialize(self) -> torch.Tensor:
+        down, mid = self.rset.materialize()
+        return mid if self.index == self.rset.n_res - 1 else down[self.index]
 
 
 class RemoteResidualSet(ResidualSet):

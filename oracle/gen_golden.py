@@ -176,7 +176,37 @@ def main():
     out = {f"down{i}": d for i, d in enumerate(down)}
     out["mid"] = mid
     _save("residual_layout", seed=SEED, b=b, f=f, **out)
+    gen_ip_adapter()
+
+
+def gen_ip_adapter():
+    """IP-Adapter dual-KV cross-attention: the reference's own IPAttnProcessor2_0 / IPAttnProcessor
+    (modules/attention_processor.py:367-492, :80-183) driving the shim's Attention module (config 4: 77 + 4 tokens)."""
+    _import_reference()
+    from oracle import synth
+    from diffusers.models.attention_processor import Attention
+    from modules.attention_processor import IPAttnProcessor, IPAttnProcessor2_0
+    torch.set_grad_enabled(False)
+    SEED = 4321
+    out = {}
+    for cname, (c, cross, heads, n, d, L, ntok, scale) in {"c64": (64, 48, 8, 3, 20, 11, 4, 1.0), "c320": (320, 768, 8, 2, 12, 81, 4, 0.6)}.items():
+        attn = Attention(query_dim=c, cross_attention_dim=cross, heads=heads, dim_head=c // heads)
+        synth.fill_module_(attn, SEED)
+        proc = IPAttnProcessor2_0(hidden_size=c, cross_attention_dim=cross, scale=scale, num_tokens=ntok)
+        synth.fill_module_(proc, SEED + 1)
+        x = synth.tensor(SEED, f"ip.{cname}.x", (n, d, c))
+        ctx = synth.tensor(SEED, f"ip.{cname}.ctx", (n, L, cross))
+        y = proc(attn, x, encoder_hidden_states=ctx)
+        proc_math = IPAttnProcessor(hidden_size=c, cross_attention_dim=cross, scale=scale, num_tokens=ntok)
+        proc_math.load_state_dict(proc.state_dict())
+        y_math = proc_math(attn, x, encoder_hidden_states=ctx)
+        assert torch.allclose(y, y_math, atol=2e-5, rtol=1e-5), (y - y_math).abs().max()
+        out[cname] = y
+    _save("ip_adapter", seed=SEED, **out)
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "ip":
+        gen_ip_adapter()
+    else:
+        main()

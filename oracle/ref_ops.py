@@ -125,6 +125,18 @@ def attention_processor(x: Tensor, wq: Tensor, wk: Tensor, wv: Tensor, wo: Tenso
     return F.linear(attention_core(q, k, v, heads), wo, bo)
 
 
+def ip_attention_processor(x: Tensor, ctx: Tensor, wq: Tensor, wk: Tensor, wv: Tensor, wo: Tensor, bo: Tensor, wk_ip: Tensor,
+                           wv_ip: Tensor, heads: int, num_tokens: int = 4, scale: float = 1.0) -> Tensor:
+    """`IPAttnProcessor2_0.__call__` modules/attention_processor.py:367-492 (IP-Adapter): the last `num_tokens` context
+    rows are image tokens with their own K/V projections; the two attention outputs are summed with `scale` (:476)."""
+    end = ctx.shape[1] - num_tokens                                                                  # :433-437
+    text, img = ctx[:, :end], ctx[:, end:]
+    q = F.linear(x, wq)
+    o = attention_core(q, F.linear(text, wk), F.linear(text, wv), heads)                             # :442-459
+    o_ip = attention_core(q, F.linear(img, wk_ip), F.linear(img, wv_ip), heads)                      # :462-474
+    return F.linear(o + scale * o_ip, wo, bo)                                                        # :476-481
+
+
 def versatile_attention(h: Tensor, video_length: int, pe: Optional[Tensor], wq, wk, wv, wo, bo, heads: int) -> Tensor:
     """`VersatileAttention.forward` motion_module.py:272-329 for attention_mode="Temporal", self-attn.
 

@@ -41,11 +41,15 @@ def time_embedding(sd: Dict[str, Tensor], t_emb: Tensor, cond: Optional[Tensor] 
     return F.linear(F.silu(h), sd[prefix + "linear_2.weight"], sd[prefix + "linear_2.bias"])
 
 
-def spatial_transformer(x: Tensor, ctx: Tensor, sd: Dict[str, Tensor], prefix: str, heads: int, groups: int = 32) -> Tensor:
+def spatial_transformer(x: Tensor, ctx: Tensor, sd: Dict[str, Tensor], prefix: str, heads: int, groups: int = 32,
+                        ip: Optional[dict] = None) -> Tensor:
     """`Transformer3DModel.forward` attention.py:120-167 (use_linear_projection False) with one
     `BasicTransformerBlock` (:254-300: self-attn, cross-attn, GEGLU FF; no temporal attention).
 
     x [b,c,f,h,w]; ctx [b, n, cross_dim] is repeated over frames (:125).
+    ip = dict(sd=..., num_tokens=4, scale=1.0): attn2 runs the IP-Adapter processor (modules/attention_processor.py:367-492,
+    installed on every cross-attention by modules/ip_adapter.py:95-126); its weights are keyed
+    `<prefix>transformer_blocks.0.attn2.processor.to_{k,v}_ip.weight` in ip["sd"].
     """
     b, c, f, hh, ww = x.shape
     g = R.groupnorm(x, sd[prefix + "norm.weight"], sd[prefix + "norm.bias"], groups, 1e-6, per_frame=True)
@@ -62,7 +66,13 @@ def spatial_transformer(x: Tensor, ctx: Tensor, sd: Dict[str, Tensor], prefix: s
     n = F.layer_norm(h, (c,), sd[t + "norm1.weight"], sd[t + "norm1.bias"], 1e-5)
     h = attn("attn1", n, None) + h
     n = F.layer_norm(h, (c,), sd[t + "norm2.weight"], sd[t + "norm2.bias"], 1e-5)
-    h = attn("attn2", n, ctx_f) + h
+    if ip is None:
+        h = attn("attn2", n, ctx_f) + h
+    else:
+        a = t + "attn2."
+        h = R.ip_attention_processor(n, ctx_f, sd[a + "to_q.weight"], sd[a + "to_k.weight"], sd[a + "to_v.weight"],
+                                     sd[a + "to_out.0.weight"], sd[a + "to_out.0.bias"], ip["sd"][a + "processor.to_k_ip.weight"],
+                                     ip["sd"][a + "processor.to_v_ip.weight"], heads, ip["num_tokens"], ip["scale"]) + h
     n = F.layer_norm(h, (c,), sd[t + "norm3.weight"], sd[t + "norm3.bias"], 1e-5)
     h = R.geglu_feedforward(n, sd[t + "ff.net.0.proj.weight"], sd[t + "ff.net.0.proj.bias"],
                             sd[t + "ff.net.2.weight"], sd[t + "ff.net.2.bias"]) + h
@@ -82,8 +92,8 @@ def _upsample_nearest(x: Tensor, size: Optional[Tuple[int, int]]) -> Tensor:
 def unet3d_forward(sd: Dict[str, Tensor], cfg: dict, sample: Tensor, timestep, encoder_hidden_states: Tensor,
                    down_block_additional_residuals: Optional[Sequence[Tensor]] = None,
                    mid_block_additional_residual: Optional[Tensor] = None,
-                   timestep_cond: Optional[Tensor] = None) -> Tensor:
-    """`UNet3DConditionModel.forward` unet.py:458-621.  sample [b,4,f,h,w] -> [b,4,f,h,w]."""
+                   timestep_cond: Optional[Tensor] = None, ip: Optional[dict] = None) -> Tensor:
+    """`UNet3DConditionModel.forward` unet.py:458-621.  sample [b,4,f,h,w] -> [b,4,f,h,w].  `ip`: see spatial_transformer."""
     boc = tuple(cfg["block_out_channels"])
     lpb = cfg["layers_per_block"]
     groups, eps = cfg["norm_num_groups"], cfg["norm_eps"]
@@ -115,7 +125,7 @@ def unet3d_forward(sd: Dict[str, Tensor], cfg: dict, sample: Tensor, timestep, e
         for j in range(lpb):
             x = resnet(x, p + f"resnets.{j}.")
             if btype == "CrossAttnDownBlock3D":
-                x = spatial_transformer(x, encoder_hidden_states, sd, p + f"attentions.{j}.", heads, groups)
+                x = spatial_transformer(x, encoder_hidden_states, sd, p + f"attentions.{j}.", heads, groups, ip)
             x = motion(x, p + f"motion_modules.{j}.", mm)
             skips.append(x)
         if i != len(boc) - 1:
@@ -126,7 +136,7 @@ def unet3d_forward(sd: Dict[str, Tensor], cfg: dict, sample: Tensor, timestep, e
         skips = [s + r for s, r in zip(skips, down_block_additional_residuals)]
 
     x = resnet(x, "mid_block.resnets.0.")                                                    # unet_blocks.py:273-280
-    x = spatial_transformer(x, encoder_hidden_states, sd, "mid_block.attentions.0.", heads, groups)
+    x = spatial_transformer(x, encoder_hidden_states, sd, "mid_block.attentions.0.", heads, groups, ip)
     x = motion(x, "mid_block.motion_modules.0.", use_mm and cfg.get("motion_module_mid_block", False))
     x = resnet(x, "mid_block.resnets.1.")
     if mid_block_additional_residual is not None:                                            # :584-585
@@ -143,7 +153,7 @@ def unet3d_forward(sd: Dict[str, Tensor], cfg: dict, sample: Tensor, timestep, e
             x = torch.cat([x, res.pop()], dim=1)
             x = resnet(x, p + f"resnets.{j}.")
             if btype == "CrossAttnUpBlock3D":
-                x = spatial_transformer(x, encoder_hidden_states, sd, p + f"attentions.{j}.", heads, groups)
+                x = spatial_transformer(x, encoder_hidden_states, sd, p + f"attentions.{j}.", heads, groups, ip)
             x = motion(x, p + f"motion_modules.{j}.", mm)
         if not final:
             x = _upsample_nearest(x, up_size)
@@ -292,6 +302,18 @@ def controlnet_shapes(cfg: dict) -> Dict[str, Tuple[int, ...]]:
     s.update(_transformer_shapes("mid_block.attentions.0.", c, cross))
     s.update(_resnet_shapes("mid_block.resnets.1.", c, c, temb))
     s["controlnet_mid_block.weight"], s["controlnet_mid_block.bias"] = (c, c, 1, 1), (c,)
+    return s
+
+
+def ip_adapter_shapes(cfg: dict) -> Dict[str, Tuple[int, ...]]:
+    """`to_k_ip` / `to_v_ip` of every cross-attention processor (modules/ip_adapter.py:95-126), keyed like `attn_processors`."""
+    s = {}
+    for k in unet3d_shapes(cfg):
+        if k.endswith("attn2.to_k.weight"):
+            c = unet3d_shapes(cfg)[k][0]
+            base = k[:-len("to_k.weight")] + "processor."
+            s[base + "to_k_ip.weight"] = (c, cfg["cross_attention_dim"])
+            s[base + "to_v_ip.weight"] = (c, cfg["cross_attention_dim"])
     return s
 
 

@@ -102,12 +102,18 @@ def test_state_dict_keys_match_reference_tables():
     assert pe.dtype == torch.float32 and un.conv_in.weight.dtype == torch.bfloat16
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference checkout (build container only)")
+def _have_reference():
+    from oracle import ref_import
+    return ref_import.reference_root() is not None
+
+
+@pytest.mark.skipif(not _have_reference(), reason="needs the reference sources (/root/reference or baseline/_ref)")
 def test_install_into_unmodified_reference_unet():
     """install() swaps the reference's own modules for B200 ones with identical state_dicts and keeps the 90-entry
     processor protocol (boundary B1/B2/B4).  Structural only: there is no GPU here and no CPU fallback to run."""
+    from oracle import ref_import
     shim = os.path.join(ROOT, "oracle", "diffusers_shim")
-    sys.path[:0] = [shim, "/root/reference"]
+    ref_root = ref_import.import_reference()
     try:
         from animatediff.models.unet import UNet3DConditionModel as RefUNet
         from controlanimate_b200.install import install, verify_installed
@@ -117,7 +123,7 @@ def test_install_into_unmodified_reference_unet():
         synth.fill_module_(ref, 1)
         before = {k: v.clone() for k, v in ref.state_dict().items()}
         counts = install(ref)
-        assert counts == dict(processors=42, motion_modules=21, resnets=22)
+        assert counts == dict(processors=42, motion_modules=21, resnets=22, controlnet_pipeline=0)
         after = ref.state_dict()
         assert set(after) == set(before) and all(torch.equal(after[k], before[k]) for k in before)
         assert len(ref.attn_processors) == 90 and verify_installed(ref)
@@ -126,7 +132,7 @@ def test_install_into_unmodified_reference_unet():
         temporal = [p for k, p in ref.attn_processors.items() if "motion_modules" in k]
         assert all(isinstance(p, B200TemporalAttnProcessor) for p in temporal)
     finally:
-        for p in (shim, "/root/reference"):
+        for p in (shim, ref_root):
             if p in sys.path:
                 sys.path.remove(p)
         for m in [m for m in sys.modules if m.split(".")[0] in ("diffusers", "animatediff", "modules", "controlnet_aux")]:

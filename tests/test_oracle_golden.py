@@ -108,3 +108,20 @@ def test_residual_layout_vs_reference(golden):
     down_g, mid_g = R.merge_controlnet_residuals([raw], [2.0], f, guess_mode=True)
     _close(down_g[0], 0.2 * g["down0"], atol=1e-6)   # logspace(-1,0,13)[0] = 0.1
     _close(mid_g, 2.0 * g["mid"], atol=1e-6)          # last factor = 1
+
+
+def test_ip_adapter_processor_vs_reference(golden):
+    """oracle.ref_ops.ip_attention_processor == the reference's IPAttnProcessor2_0 (attention_processor.py:367-492) run
+    through the shim's Attention module (fixture: oracle/gen_golden.py gen_ip_adapter)."""
+    from oracle import ref_unet3d as U
+    g = golden("ip_adapter")
+    seed = int(g["seed"])
+    for cname, (c, cross, heads, n, d, L, ntok, scale) in {"c64": (64, 48, 8, 3, 20, 11, 4, 1.0), "c320": (320, 768, 8, 2, 12, 81, 4, 0.6)}.items():
+        sd = U.synth_state_dict({"to_q.weight": (c, c), "to_k.weight": (c, cross), "to_v.weight": (c, cross), "to_out.0.weight": (c, c),
+                                 "to_out.0.bias": (c,)}, seed)
+        ip = U.synth_state_dict({"to_k_ip.weight": (c, cross), "to_v_ip.weight": (c, cross)}, seed + 1)
+        x = synth.tensor(seed, f"ip.{cname}.x", (n, d, c))
+        ctx = synth.tensor(seed, f"ip.{cname}.ctx", (n, L, cross))
+        y = R.ip_attention_processor(x, ctx, sd["to_q.weight"], sd["to_k.weight"], sd["to_v.weight"], sd["to_out.0.weight"],
+                                     sd["to_out.0.bias"], ip["to_k_ip.weight"], ip["to_v_ip.weight"], heads, ntok, scale)
+        assert torch.allclose(y, torch.from_numpy(g[cname]), atol=3e-5, rtol=1e-4), cname
