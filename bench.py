@@ -39,6 +39,9 @@ LATENT = 64
 GUIDANCE = 7.5
 COND_SCALE = [1.0, 0.5]
 OVERLAP = 4
+# --workload config3 (BASELINE configs[2]): LCM-LoRA branch (b = 1, guidance through timestep_cond), 4 ControlNets with
+# SampleConfig.yaml's scales, 4 steps, 16-frame windows with 4-frame overlap (5 windows = the 64-frame clip)
+CONFIG3 = dict(steps=4, guidance=1.1, cond_scale=[1.0, 0.35, 1.0, 0.4])
 
 
 def ncu_traffic(family: str):
@@ -298,15 +301,21 @@ def run_b200(args):
     torch.backends.cudnn.benchmark = True
 
     mode = args.parallelism if world > 1 else "single"
-    cfg = utils.sd15_unet3d_config()
+    lcm = args.workload == "config3"
+    n_steps = CONFIG3["steps"] if lcm else DDIM_STEPS
+    cond_scale = CONFIG3["cond_scale"] if lcm else COND_SCALE
+    guidance = CONFIG3["guidance"] if lcm else GUIDANCE
+    n_nets = len(cond_scale)
+    cfg = utils.sd15_unet3d_config(time_cond_proj_dim=256 if lcm else None)
     dtype = torch.bfloat16
     unet = utils.build_on_device(lambda: un.UNet3DConditionModel(**cfg), dev, dtype, seed=1)
-    nets = [utils.build_on_device(lambda: un.ControlNetModel(), dev, dtype, seed=2 + k) for k in range(2)]
-    mc = pipeline.MultiControlNetResiduals(nets, COND_SCALE)
+    nets = [utils.build_on_device(lambda: un.ControlNetModel(), dev, dtype, seed=2 + k) for k in range(n_nets)]
+    mc = pipeline.MultiControlNetResiduals(nets, cond_scale)
     sched = pipeline.DDIMScheduler()
-    timesteps = sched.set_timesteps(DDIM_STEPS)
-    step_par = parallel.StepParallel(mode, rank, world, n_nets=2) if mode in parallel.StepParallel.MODES else None
-    loop = pipeline.DenoisingLoop(unet, mc, sched, guidance_scale=GUIDANCE, use_cuda_graph=not args.no_graph, parallel=step_par)
+    timesteps = sched.set_timesteps(n_steps)
+    step_par = parallel.StepParallel(mode, rank, world, n_nets=n_nets) if mode in parallel.StepParallel.MODES else None
+    loop = pipeline.DenoisingLoop(unet, mc, sched, guidance_scale=guidance, use_cuda_graph=not args.no_graph, parallel=step_par,
+                                  use_lcm=lcm)
     windows = parallel.WindowParallel(rank, world, FRAMES, OVERLAP) if mode == "windows" else None
 
     f, lat = FRAMES, args.latent
@@ -314,14 +323,15 @@ def run_b200(args):
     g = torch.Generator(device="cpu").manual_seed(100 + (rank if mode == "windows" else 0))
     # host-side inputs (pinned): what a caller of the public API holds
     h_latents = torch.randn(1, 4, f, lat, lat, generator=g).pin_memory()
-    h_prompt = torch.randn(2, 77, 768, generator=g).to(dtype).pin_memory()
-    h_images = [torch.randn(2 * f, 3, lat * 8, lat * 8, generator=g).to(dtype) for _ in range(2)]
+    rows = 1 if lcm else 2                                      # CFG duplicates the batch; the LCM branch does not
+    h_prompt = torch.randn(rows, 77, 768, generator=g).to(dtype).pin_memory()
+    h_images = [torch.randn(rows * f, 3, lat * 8, lat * 8, generator=g).to(dtype) for _ in range(n_nets)]
     mc.prep_images = [im.to(dev) for im in h_images]          # prepared once per window (prep_control_images)
     d_prompt = h_prompt.to(dev)
     h_out = torch.empty_like(h_latents).pin_memory()
 
     def one_step(latents, i):
-        t = timesteps[i % DDIM_STEPS]
+        t = timesteps[i % n_steps]
         latents = loop.step(latents, t, d_prompt)
         if windows is not None:
             latents = windows.exchange(latents)
@@ -364,7 +374,7 @@ def run_b200(args):
     for i in range(args.steps):
         d_lat = h_latents.to(dev, non_blocking=True)
         d_p = h_prompt.to(dev, non_blocking=True)
-        out = loop.step(d_lat, timesteps[i % DDIM_STEPS], d_p)
+        out = loop.step(d_lat, timesteps[i % n_steps], d_p)
         if windows is not None:
             out = windows.exchange(out)
         h_out.copy_(out, non_blocking=True)
@@ -418,8 +428,8 @@ def run_b200(args):
             scaling = "strong"
             par_desc = {"cfg": "CFG halves x2 (one window)", "controlnet": f"UNet rank + {world - 1} ControlNet rank(s) (one window)",
                         "cfg+controlnet": f"CFG halves x (UNet rank + {world // 2 - 1} ControlNet rank(s)) (one window)"}[mode]
-        value = unique / (DDIM_STEPS * ms * 1e-3)
-        e2e = unique / (DDIM_STEPS * ms_e2e * 1e-3)
+        value = unique / (n_steps * ms * 1e-3)
+        e2e = unique / (n_steps * ms_e2e * 1e-3)
         top = kern["dominant"]
         top["traffic"] = ncu_traffic(top["kernel"])
         top["traffic_source"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu launch list of the same step (profiles/)"
@@ -427,12 +437,17 @@ def run_b200(args):
             "metric": "denoised frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(args, parallelism=par_desc),
+            "config": workload_config(args, parallelism=par_desc) if not lcm else {
+                "workload": f"config 3: SD1.5 UNet3D (time_cond_proj_dim 256) + motion modules + 4 ControlNets {cond_scale}, LCM branch (b=1, "
+                            f"guidance {guidance} through timestep_cond), {FRAMES}-frame windows 512x512 (latent {args.latent}x{args.latent}), "
+                            f"{n_steps} steps; one bench step = one denoising step; scheduler arithmetic = DDIM update (the LCM scheduler is "
+                            "outside the hot path)", "frames_per_window": FRAMES, "steps": n_steps, "controlnets": n_nets,
+                "cond_scale": cond_scale, "parallelism": par_desc, "window_overlap_frames": OVERLAP},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h_latents.numel() * 4 + h_prompt.numel() * 2, "d2h_bytes_per_step": h_out.numel() * 4},
             "frames_unique": unique, "frames_counted": counted,
-            "frames_counted_per_s": counted / (DDIM_STEPS * ms * 1e-3),
+            "frames_counted_per_s": counted / (n_steps * ms * 1e-3),
             # kernels of libca_b200.so executed inside the timed region (counted per launch in eager mode; with CUDA-graph
             # replay = launches recorded in one captured step x timed steps)
             "gpu_launches": launches if launches else kern["launches_per_step"] * args.steps,
@@ -444,12 +459,12 @@ def run_b200(args):
         }
         if step_par is not None and step_par.g > 1:
             # bytes kernel (3) pulls over NVLink per step on each UNet rank: the raw residual sets of the sharded ControlNets
-            rows = (1 if step_par.halves == 2 else 2) * f
+            rows_cn = (1 if (step_par.halves == 2 or lcm) else 2) * f
             per_net = sum(c * (lat // d) * (lat // d) for c, d in ((320, 1),) * 3 + ((320, 2),) + ((640, 2),) * 2 + ((640, 4),)
-                          + ((1280, 4),) * 2 + ((1280, 8),) * 4) * rows * 2
-            line["nvlink_bytes_per_step_per_unet_rank"] = per_net * 2
+                          + ((1280, 4),) * 2 + ((1280, 8),) * 4) * rows_cn * 2
+            line["nvlink_bytes_per_step_per_unet_rank"] = per_net * n_nets
         extra = {}
-        if args.eager_yardstick and world == 1:
+        if args.eager_yardstick and world == 1 and not lcm:
             del loop, unet, nets, mc
             torch.cuda.empty_cache()
             try:
@@ -458,7 +473,7 @@ def run_b200(args):
                 extra["torch_eager_gpu"] = {"error": f"{type(e).__name__}: {e}"[:200]}
         if extra:
             line["extra"] = extra
-        if args.cpu_baseline and world == 1:
+        if args.cpu_baseline and world == 1 and not lcm:
             step, desc, kind = cpu_reference_step_factory(args.cpu_frames, args.latent)
             t0 = time.perf_counter()
             step()
@@ -479,6 +494,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--latent", type=int, default=LATENT)
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames of the bounded CPU sample (>= 4: temporal attention is real)")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3"],
+                    help="config2 = the headline (BASELINE configs[1]); config3 = LCM + 4 ControlNets, 4 steps (configs[2])")
     ap.add_argument("--parallelism", default="windows", choices=["windows", "cfg", "controlnet", "cfg+controlnet"],
                     help="how N > 1 GPUs are used (see the module docstring)")
     ap.add_argument("--no-eager-yardstick", dest="eager_yardstick", action="store_false",

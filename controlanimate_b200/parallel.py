@@ -167,6 +167,7 @@ class StepParallel:
             self.halves, self.g = 2, world // 2
         if self.g > 1 and (self.g - 1 > n_nets or n_nets < 1):
             raise ValueError(f"{self.g - 1} ControlNet ranks per CFG half for {n_nets} nets: a rank without a net has nothing to do")
+        self.rows_per_unet = 2               # batch rows a UNet rank returns when CFG is not split (1 in the LCM branch)
         self.half = rank // self.g           # which CFG row(s) this rank works on
         self.role = rank % self.g            # 0 = UNet rank of the half
 
@@ -208,12 +209,14 @@ class StepParallel:
         if noise_local is not None:
             mine = noise_local.contiguous()
         else:
-            mine = torch.zeros((1 if self.halves == 2 else 2, *like.shape[1:]), dtype=like.dtype, device=like.device)
+            mine = torch.zeros((1 if self.halves == 2 else self.rows_per_unet, *like.shape[1:]), dtype=like.dtype, device=like.device)
         parts = [torch.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(parts, mine, group=self.group)
         rows = [parts[r] for r in self.unet_ranks()]
         if self.halves == 2:
             return rows[0] + guidance_scale * (rows[1] - rows[0])
+        if rows[0].shape[0] == 1:        # LCM branch: a single row, the guidance scale went in through timestep_cond
+            return rows[0]
         u, c = rows[0].chunk(2)
         return u + guidance_scale * (c - u)
 

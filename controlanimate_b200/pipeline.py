@@ -50,6 +50,18 @@ class DDIMScheduler:
         return sp * x0 + s1p * noise_pred
 
 
+def get_w_embedding(w: torch.Tensor, embedding_dim: int = 256, dtype=torch.float32) -> torch.Tensor:
+    """LCM guidance-scale embedding (reference controlanimation_pipeline.py:477-498): sinusoidal features of 1000 w, fed to
+    `time_embedding.cond_proj` as `timestep_cond` (unet.py:526-534)."""
+    if w.dim() != 1:
+        raise ValueError("w must be 1-D")
+    half = embedding_dim // 2
+    freq = torch.exp(torch.arange(half, dtype=dtype, device=w.device) * -(torch.log(torch.tensor(10000.0)) / (half - 1)))
+    emb = (w.to(dtype) * 1000.0)[:, None] * freq[None, :]
+    emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=1)
+    return torch.nn.functional.pad(emb, (0, 1)) if embedding_dim % 2 == 1 else emb
+
+
 class MultiControlNetResiduals:
     """Mirror of MultiControlNetResidualsPipeline.__call__ (modules/controlresiduals_pipeline.py:278-316) for N native
     ControlNets.  `prep_images[k]` is the prepared control video of net k as [(b f), 3, H, W] (what
@@ -98,24 +110,41 @@ class DenoisingLoop:
     """
 
     def __init__(self, unet: UNet3DConditionModel, controlnets: Optional[MultiControlNetResiduals], scheduler: DDIMScheduler,
-                 guidance_scale: float = 7.5, guess_mode: bool = False, use_cuda_graph: bool = False, parallel=None):
+                 guidance_scale: float = 7.5, guess_mode: bool = False, use_cuda_graph: bool = False, parallel=None,
+                 use_lcm: bool = False):
         """parallel: a `parallel.StepParallel` — this window's step is split over its ranks (CFG halves and / or ControlNet
-        sharding over NVLink); every rank of the group must call `step` with the same latents."""
+        sharding over NVLink); every rank of the group must call `step` with the same latents.
+        use_lcm: the LCM branch of the loop (controlanimation_pipeline.py:770-771, 823-833): no CFG duplication (b = 1), the
+        guidance scale enters through `timestep_cond = get_w_embedding(guidance_scale)`, prompt_embeds is the positive prompt
+        [1, L, D].  (The LCM scheduler itself is outside the hot path; `scheduler.step` is applied to the model output.)"""
         self.unet, self.controlnets, self.scheduler = unet, controlnets, scheduler
         self.guidance_scale, self.guess_mode = guidance_scale, guess_mode
+        self.use_lcm = use_lcm
+        if use_lcm and parallel is not None and parallel.halves == 2:
+            raise ValueError("the LCM branch has no CFG halves to split")
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
         self.parallel = parallel
         self._transport = None
         if parallel is not None:
-            if guess_mode or guidance_scale <= 1.0:
+            parallel.rows_per_unet = 1 if use_lcm else 2
+            if guess_mode or (guidance_scale <= 1.0 and not use_lcm):
                 raise ValueError("step parallelism covers the CFG path without guess mode (BASELINE configs 2-4)")
             if parallel.g > 1 and controlnets is None:
                 raise ValueError("ControlNet sharding needs a ControlNet set")
 
     @property
     def do_cfg(self):
-        return self.guidance_scale > 1.0
+        return self.guidance_scale > 1.0 and not self.use_lcm
+
+    def _w_embedding(self, latents: torch.Tensor) -> Optional[torch.Tensor]:
+        if not self.use_lcm:
+            return None
+        dim = self.unet.config.get("time_cond_proj_dim")
+        if not dim:
+            raise ValueError("use_lcm needs a UNet built with time_cond_proj_dim (LCM checkpoints: 256)")
+        w = torch.full((latents.shape[0],), float(self.guidance_scale), device=latents.device)
+        return get_w_embedding(w, dim).to(self.unet.conv_in.weight.dtype)
 
     def predict_noise(self, latents: torch.Tensor, t, prompt_embeds: torch.Tensor) -> torch.Tensor:
         """Guided noise prediction for latents [1,4,f,h,w]; `t` is an int or a 1-element int64 device tensor."""
@@ -132,7 +161,8 @@ class DenoisingLoop:
                                          prompt_embeds[-1:] if single else prompt_embeds, f,
                                          do_classifier_free_guidance=cfg, guess_mode=self.guess_mode)
         noise = self.unet(model_in, t, encoder_hidden_states=prompt_embeds, down_block_additional_residuals=down,
-                          mid_block_additional_residual=mid).sample.to(latents.dtype)                   # :836-841
+                          mid_block_additional_residual=mid, timestep_cond=self._w_embedding(model_in)
+                          ).sample.to(latents.dtype)                                                     # :823-841
         if cfg:
             u, c = noise.chunk(2)
             noise = u + self.guidance_scale * (c - u)                                                    # :845-846
@@ -161,7 +191,7 @@ class DenoisingLoop:
             from .parallel import SymmetricResiduals
             from .residuals import N_RESIDUALS  # noqa: F401
             f, hh, ww = latents.shape[2], latents.shape[3], latents.shape[4]
-            rows = (1 if sp.halves == 2 else 2) * f
+            rows = (1 if (sp.halves == 2 or self.use_lcm) else 2) * f
             cn = self.controlnets.controlnets[0]
             boc, lpb = cn.config["block_out_channels"], cn.config["layers_per_block"]
             shapes, h, w = [(rows, boc[0], hh, ww)], hh, ww
@@ -183,7 +213,7 @@ class DenoisingLoop:
         return their CFG row(s) of the UNet output, ControlNet ranks publish their residuals and return None."""
         sp, mc = self.parallel, self.controlnets
         f = latents.shape[2]
-        model_in = latents if sp.halves == 2 else torch.cat([latents] * 2)
+        model_in = latents if (sp.halves == 2 or self.use_lcm) else torch.cat([latents] * 2)
         prompt = sp.rows(prompt_embeds)
         # the ControlNets always see BOTH prompts: row n of the (b f) batch takes prompt n % 2 (the tiling quirk of
         # controlresiduals_pipeline.py:292 is part of the reference's arithmetic), n counted over the full CFG batch
@@ -210,7 +240,8 @@ class DenoisingLoop:
                 per_net.append(tr.peer_views(owner, slot))
                 owners.append(owner)
             down = RemoteResidualSet(per_net, mc.cond_scale, f, False, tr, owners)
-        return self.unet(model_in, t, encoder_hidden_states=prompt, down_block_additional_residuals=down).sample.to(latents.dtype)
+        return self.unet(model_in, t, encoder_hidden_states=prompt, down_block_additional_residuals=down,
+                         timestep_cond=self._w_embedding(model_in)).sample.to(latents.dtype)
 
     def _graphed_noise(self, latents, t: int, prompt_embeds):
         mc = self.controlnets

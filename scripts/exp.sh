@@ -1,6 +1,3 @@
-( time timeout 1500 python -m pytest tests -m gpu -q -x ) > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-LAB_CUBLAS=1 timeout 200 python scripts/gemm_lab.py final > gpurun_out/lab_final.log 2>&1
-timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
-echo "bench exit $?" >> gpurun_out/bench.err
-tail -5 gpurun_out/pytest_gpu.log; cut -c1-300 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+( timeout 1500 python -m pytest tests/test_gpu_fullwidth.py -q -x -s ) > gpurun_out/pytest_fullwidth.log 2>&1
+grep -n "full width\|fp16\|lcm\|config 3\|passed\|failed\|Error" gpurun_out/pytest_fullwidth.log | head
+timeout 900 python bench.py --workload config3 --steps 5 --warmup 3 > gpurun_out/bench_config3.json 2> gpurun_out/bench_config3.err; echo "bench c3 exit $?"; cut -c1-300 gpurun_out/bench_config3.json; tail -3 gpurun_out/bench_config3.err

@@ -200,3 +200,42 @@ def test_unet3d_timestep_cond_lcm(ca):
     print(f"[lcm] UNet3D with timestep_cond: cosine {c:.6f} (cosine of the oracle with vs without the embedding: {cosine(ref, ref_nocond):.4f})")
     assert c >= 0.999, c
     assert cosine(ref, ref_nocond) < 0.9999   # the guidance embedding matters, so the agreement above is not vacuous
+
+
+def test_denoising_step_config3_lcm_four_controlnets(ca):
+    """BASELINE config 3, one window-step: LCM branch (b = 1, guidance through timestep_cond; controlanimation_pipeline.py:
+    770-771, 823-833), FOUR ControlNets with SampleConfig's scales [1.0, 0.35, 1.0, 0.4] merged by kernel (3) in one pass,
+    16 frames — against the oracle (tiny width: four full-width nets would only repeat test_denoising_step_full_width)."""
+    cfg = _tiny_cfg(time_cond_proj_dim=256)
+    f, hh, t, w_guid = 16, 16, 759, 1.1
+    scales = [1.0, 0.35, 1.0, 0.4]
+    unet = ca.unet.UNet3DConditionModel(**cfg)
+    sd_u = load_synth(unet, U.unet3d_shapes(cfg), SEED)
+    unet = unet.cuda().bfloat16().eval()
+    nets, sds = [], []
+    for k in range(4):
+        cn = ca.unet.ControlNetModel(block_out_channels=cfg["block_out_channels"], cross_attention_dim=cfg["cross_attention_dim"])
+        sds.append(load_synth(cn, U.controlnet_shapes(cfg), SEED + 10 + k))
+        nets.append(cn.cuda().bfloat16().eval())
+    latents = r16(synth.tensor(SEED, "c3.lat", (1, 4, f, hh, hh)))
+    prompt = r16(synth.tensor(SEED, "c3.ctx", (1, 77, cfg["cross_attention_dim"])))
+    images = [r16(synth.tensor(SEED, f"c3.img{k}", (f, 3, hh * 8, hh * 8), 0.5)) for k in range(4)]
+    w_emb = ca.pipeline.get_w_embedding(torch.full((1,), w_guid), 256)
+    # oracle
+    x2d = latents.permute(0, 2, 1, 3, 4).reshape(f, 4, hh, hh)
+    per_net = [U.controlnet_forward(sds[k], cfg, x2d, t, torch.cat([prompt] * f), images[k]) for k in range(4)]
+    down, mid = R.merge_controlnet_residuals(per_net, scales, f)
+    want = U.unet3d_forward(sd_u, cfg, latents, t, prompt, down, mid, timestep_cond=r16(w_emb))
+    # product
+    mc = ca.pipeline.MultiControlNetResiduals(nets, scales)
+    mc.prep_images = [im.cuda().bfloat16() for im in images]
+    sched = ca.pipeline.DDIMScheduler()
+    sched.set_timesteps(4)
+    loop = ca.pipeline.DenoisingLoop(unet, mc, sched, guidance_scale=w_guid, use_lcm=True)
+    with torch.no_grad():
+        got = loop.predict_noise(latents.cuda().bfloat16(), t, prompt.cuda().bfloat16())
+        nxt = loop.step(latents.cuda(), t, prompt.cuda().bfloat16())
+    c = cosine(got, want)
+    print(f"[config 3] LCM step, 4 ControlNets, b=1, f=16: model-output cosine {c:.6f}")
+    assert got.shape == (1, 4, f, hh, hh) and c >= 0.999, c
+    assert torch.isfinite(nxt).all() and nxt.shape == latents.shape
