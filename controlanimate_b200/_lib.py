@@ -27,6 +27,7 @@ SIGNATURES = {
     "ca_residual_merge": (_i, [C.POINTER(_vp), C.POINTER(_f), C.POINTER(_vp), C.POINTER(_i), _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ca_layernorm_pe": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _f, _i, _vp]),
     "ca_temporal_attn_core": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _f, _i, _vp]),
+    "ca_temporal_attn_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _i, _vp]),
     "ca_cross_attn_core": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _vp, _f, _i, _vp]),
     "ca_bias_act_residual": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _f, _i, _i, _vp]),
     "ca_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _ll, _ll, _i, _i, _vp]),

@@ -186,6 +186,13 @@ class _FusedWeights:
         return self._w
 
 
+import os as _os
+
+# CA_FUSED_TEMPORAL=1 routes the temporal-attention blocks of the 320-wide level through the one-launch kernel
+# (ca_temporal_attn_fused).  It is parity-green but, as measured in profiles/r02_fused_notes.md, still slower than the
+# four-launch block (LayerNorm+PE, QKV GEMM, attention core, out-proj GEMM: 330 vs 250 us at 64x64), so it is opt-in.
+_FUSED_TEMPORAL = _os.environ.get("CA_FUSED_TEMPORAL", "0") == "1"
+
 # --------------------------------------------------------------------------------------------------
 # B1: AttentionProcessor for VersatileAttention (temporal self-attention)
 # --------------------------------------------------------------------------------------------------
@@ -303,6 +310,23 @@ class TemporalAttention(nn.Module):
     def get_processor(self, return_deprecated_lora: bool = False):
         return self.processor
 
+    def fused_ok(self, h: torch.Tensor, f: int) -> bool:
+        """The one-launch block (ca_temporal_attn_fused) applies: a built width, our own processor, 16-bit activations."""
+        c = h.shape[-1]
+        return (_FUSED_TEMPORAL and c in ops.FUSED_TEMPORAL_WIDTHS and isinstance(self.processor, B200TemporalAttnProcessor)
+                and h.dtype in (torch.bfloat16, torch.float16) and f <= 32 and (c // self.heads) % 8 == 0 and h.is_contiguous())
+
+    def fused(self, h: torch.Tensor, norm: nn.LayerNorm, b: int, f: int, d: int) -> torch.Tensor:
+        """h + to_out(attn(LN(h) + pe)) in one launch (motion_module.py:213-219 for one attention block)."""
+        key = tuple((w._version, w.data_ptr(), w.dtype) for w in (self.to_q.weight, self.to_k.weight, self.to_v.weight))
+        if getattr(self, "_perm_key", None) != key:
+            self._perm = ops.pack_qkv_per_head(self.to_q.weight, self.to_k.weight, self.to_v.weight, self.heads)
+            self._perm_key = key
+        pe = self.pos_encoder.pe if self.pos_encoder is not None else None
+        return ops.temporal_attention_fused(h, f32(norm.weight), f32(norm.bias), f32(pe), self._perm, self.to_out[0].weight,
+                                            f32(self.to_out[0].bias), batch=b, frames=f, sites=d, heads=self.heads, eps=norm.eps,
+                                            scale=self.scale)
+
     def native(self, n_tok: torch.Tensor, residual: torch.Tensor, b: int, f: int, d: int) -> torch.Tensor:
         """to_out(attn(qkv(n_tok))) + residual on token-major rows (n_tok already LayerNorm'd + PE-added)."""
         c = n_tok.shape[-1]
@@ -347,6 +371,9 @@ class _TemporalTransformerBlock(nn.Module):
 
     def native(self, h: torch.Tensor, b: int, f: int, d: int) -> torch.Tensor:
         for attn, norm in zip(self.attention_blocks, self.norms):            # motion_module.py:213-219
+            if attn.fused_ok(h, f):                                          # kernel (1) fused: one launch per attention block
+                h = attn.fused(h, norm, b, f, d)
+                continue
             pe = attn.pos_encoder.pe if attn.pos_encoder is not None else None
             n = ops.layernorm_pe(h, f32(norm.weight), f32(norm.bias), norm.eps, pe=f32(pe), frames=f, sites=d)
             h = attn.native(n, h, b, f, d)

@@ -151,6 +151,51 @@ def temporal_attention_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *
     return o
 
 
+FUSED_TEMPORAL_WIDTHS = (64, 128, 320)   # built variants of ca_temporal_attn_fused
+
+
+def pack_qkv_per_head(wq: torch.Tensor, wk: torch.Tensor, wv: torch.Tensor, heads: int) -> torch.Tensor:
+    """[heads * nq, C] weight for ca_temporal_attn_fused: per head the hd rows of to_q, to_k, to_v, zero-padded to nq rows."""
+    c = wq.shape[0]
+    hd = c // heads
+    nq = (3 * hd + 15) // 16 * 16
+    out = torch.zeros((heads, nq, wq.shape[1]), dtype=wq.dtype, device=wq.device)
+    for i, w in enumerate((wq, wk, wv)):
+        out[:, i * hd:(i + 1) * hd] = w.detach().reshape(heads, hd, -1)
+    return out.reshape(heads * nq, -1).contiguous()
+
+
+def temporal_attention_fused(x: torch.Tensor, ln_gamma: torch.Tensor, ln_beta: torch.Tensor, pe: Optional[torch.Tensor],
+                             wqkv_perm: torch.Tensor, wo: torch.Tensor, bo: torch.Tensor, *, batch: int, frames: int, sites: int,
+                             heads: int, eps: float = 1e-5, scale: Optional[float] = None,
+                             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = x + to_out(attn(LN(x) + pe)) for token-major x [(b f d), C] in one launch (kernel 1, fused).
+    wqkv_perm = pack_qkv_per_head(to_q.weight, to_k.weight, to_v.weight, heads)."""
+    _cuda(x, ln_gamma, ln_beta, pe, wqkv_perm, wo, bo)
+    if x.dim() != 2 or not x.is_contiguous() or x.shape[0] != batch * frames * sites:
+        raise ValueError("x must be a contiguous token matrix [(b f d), C]")
+    c = x.shape[1]
+    if x.dtype not in (torch.bfloat16, torch.float16) or wqkv_perm.dtype != x.dtype or wo.dtype != x.dtype:
+        raise ValueError("temporal_attention_fused: x, wqkv_perm and wo must share bf16 or f16")
+    hd = c // heads
+    nq = (3 * hd + 15) // 16 * 16
+    if tuple(wqkv_perm.shape) != (heads * nq, c) or tuple(wo.shape) != (c, c) or not wqkv_perm.is_contiguous() or not wo.is_contiguous():
+        raise ValueError("temporal_attention_fused: bad weight shapes")
+    g32, b32, bo32, pe32 = _f32(ln_gamma), _f32(ln_beta), _f32(bo), _f32(pe)
+    if pe32 is not None:
+        pe32 = pe32.reshape(-1, c)
+        if pe32.shape[0] < frames:
+            raise ValueError(f"video has {frames} frames but the positional encoding only {pe32.shape[0]} (motion_module.py:236)")
+    y = torch.empty_like(x) if out is None else out
+    scale = hd ** -0.5 if scale is None else scale
+    T = x.shape[0]
+    with P.span("temporal_attn_fused", 1, 2.0 * x.numel() * x.element_size() + 8.0 * c * c, T * (8.0 * c * c + 4.0 * frames * c)):
+        L.check(L.load().ca_temporal_attn_fused(x.data_ptr(), y.data_ptr(), g32.data_ptr(), b32.data_ptr(), _ptr(pe32),
+                                                wqkv_perm.data_ptr(), wo.data_ptr(), bo32.data_ptr(), batch, frames, sites, c, heads,
+                                                float(eps), float(scale), _dt(x), _stream()), "ca_temporal_attn_fused")
+    return y
+
+
 def cross_attention_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, frames: int, sites: int, heads: int,
                          ctx_of_frame: Optional[torch.Tensor] = None, scale: Optional[float] = None,
                          out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -104,6 +104,23 @@ int ca_temporal_attn_core(const void* q, const void* k, const void* v, void* o, 
                           int head_dim, long long ldq, long long ldk, long long ldv, long long ldo, int seq_major,
                           float scale, int dtype, void* stream);
 
+/* Kernel (1), fused: one whole temporal-attention block in ONE launch,
+ *   y = x + to_out( attention( LayerNorm(x) * gamma + beta + pe[frame] ) ) + b_out
+ * Replaces nn.LayerNorm (motion_module.py:214), VersatileAttention.forward (:272-329: both rearranges, the positional
+ * encoding :287-288, the processor call :321), the AttentionProcessor arithmetic (modules/attention_processor.py:186-272:
+ * to_q/to_k/to_v, softmax(q k^T scale) v per head over the f frames of every site, to_out[0]) and the residual add of
+ * TemporalTransformerBlock.forward (:219).  x is read once and y written once; QKV and out projections run on tcgen05.
+ *   x, y       token-major [b*f*d, C] dense rows (row t = (b*f + frame)*d + site); y may alias x
+ *   ln_gamma, ln_beta [C] fp32; pe [>= f, C] fp32 or NULL; bo [C] fp32
+ *   wqkv_perm  [heads * nq, C] (dtype), nq = 3*head_dim rounded up to a multiple of 16: per head the rows of to_q, to_k,
+ *              to_v of that head followed by zero rows (the host packs it once per weight version)
+ *   wo         [C, C] (dtype) = to_out[0].weight
+ *   constraints: C in {64, 128, 320} (returns CA_ERR_UNSUPPORTED otherwise: 128 rows of the normalised tile and of the
+ *   attention output must both fit one SM's shared memory), head_dim % 8 == 0, f <= 32, dtype bf16/f16 */
+int ca_temporal_attn_fused(const void* x, void* y, const float* ln_gamma, const float* ln_beta, const float* pe,
+                           const void* wqkv_perm, const void* wo, const float* bo, int b, int f, int d, int C, int heads,
+                           float eps, float scale, int dtype, void* stream);
+
 /* Cross-attention core of the spatial transformer: every latent site attends to the
  * kv_len <= 96 prompt tokens, O = softmax(Q K^T * scale) V per (frame, head).
  * Replaces the attention arithmetic of BasicTransformerBlock.attn2 (reference animatediff/models/attention.py:283-289

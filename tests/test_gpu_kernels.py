@@ -361,3 +361,50 @@ def test_linear_strided_input_and_repeat(ops):
         y = ops.linear(xs, w)
         ref = torch.nn.functional.linear(xs.float().cpu(), w.float().cpu())
         assert relerr(y, ref) <= 2e-3
+
+
+FUSED_CASES = [
+    # c, f, d, b   (heads = 8)
+    (320, 16, 32, 2), (320, 16, 24, 1),      # config-2 width: hd 40, S = 8; d = 24 leaves the pair's second CTA partly empty
+    (320, 8, 40, 1), (320, 32, 12, 2),       # S = 16 / S = 4
+    (320, 24, 13, 1),                        # S = 5: 120 of 128 tile rows, ragged site tiles
+    (64, 16, 20, 2), (128, 5, 9, 1),         # narrow variants (hd 8 / 16), odd frame count
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("c,f,d,b", FUSED_CASES)
+def test_temporal_attention_fused(ops, c, f, d, b, dtype):
+    """ca_temporal_attn_fused == x + to_out(attn(LN(x) + pe)): LayerNorm (motion_module.py:214) + VersatileAttention.forward
+    (:272-329) + AttentionProcessor (attention_processor.py:186-272) + residual (:219), against the oracle."""
+    from oracle import ref_ops as R
+    heads = 8
+    T = b * f * d
+    x = synth.tensor(41, f"fu.x.{c}.{f}.{d}", (T, c)).to(dtype)
+    w = {n: synth.tensor(41, f"fu.{n}.{c}", (c, c), c ** -0.5).to(dtype) for n in ("wq", "wk", "wv", "wo")}
+    bo = synth.tensor(41, "fu.bo", (c,), 0.1)
+    gamma = 1 + synth.tensor(41, "fu.g", (c,), 0.1)
+    beta = synth.tensor(41, "fu.b", (c,), 0.1)
+    pe = R.positional_encoding(32, c)
+    # oracle: rows are (b f) d c
+    xf = x.float().reshape(b * f, d, c)
+    n = torch.nn.functional.layer_norm(xf, (c,), gamma, beta, 1e-5)
+    ref = R.versatile_attention(n, f, pe, w["wq"].float(), w["wk"].float(), w["wv"].float(), w["wo"].float(), bo, heads) + xf
+    perm = ops.pack_qkv_per_head(w["wq"].cuda(), w["wk"].cuda(), w["wv"].cuda(), heads)
+    y = ops.temporal_attention_fused(x.cuda(), gamma.cuda(), beta.cuda(), pe.cuda(), perm, w["wo"].cuda(), bo.cuda(), batch=b, frames=f,
+                                     sites=d, heads=heads)
+    # four chained roundings to the 16-bit storage type (LN output, q|k|v, attention output, result): 2x the per-op bound
+    assert relerr(y, ref.reshape(T, c)) <= 2 * REL[dtype], relerr(y, ref.reshape(T, c))
+    # in place, and deterministic
+    x2 = x.cuda().clone()
+    y2 = ops.temporal_attention_fused(x2, gamma.cuda(), beta.cuda(), pe.cuda(), perm, w["wo"].cuda(), bo.cuda(), batch=b, frames=f,
+                                      sites=d, heads=heads, out=x2)
+    assert torch.equal(y2, y)
+
+
+def test_temporal_attention_fused_rejects_unbuilt_width(ops):
+    x = torch.zeros(16 * 4, 640, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(640, 640, device="cuda", dtype=torch.bfloat16)
+    v = torch.zeros(640, device="cuda")
+    with pytest.raises(ValueError):
+        ops.temporal_attention_fused(x, v, v, None, ops.pack_qkv_per_head(w, w, w, 8), w, v, batch=1, frames=16, sites=4, heads=8)

@@ -243,3 +243,17 @@ def test_cuda_graph_replay_matches_eager_and_is_deterministic(ca):
         assert torch.equal(x, w)            # eager is deterministic
         assert cosine(x, y) >= 0.99999      # graph == eager (cuDNN may pick another algorithm under capture)
     assert len(graphed._graphs) == 1 and not torch.equal(b[0], b[1])     # timestep really changes inside the replayed graph
+
+
+def test_motion_module_through_fused_temporal_block():
+    """CA_FUSED_TEMPORAL=1 (read once per process) routes the 320-wide motion module's attention blocks through the one-launch
+    kernel ca_temporal_attn_fused; the B2 parity cases are re-run in a child process with it enabled."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("CA_FUSED_CHILD") == "1":
+        pytest.skip("already inside a child run")
+    child_env = dict(os.environ, CA_FUSED_CHILD="1", CA_FUSED_TEMPORAL="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", __file__, "-k",
+                        "test_motion_module_b2 or test_unet3d_forward"], env=child_env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
