@@ -18,9 +18,13 @@ OBJ_DIR = os.path.join(HERE, "build")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
-    "--use_fast_math", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "-Xptxas", "-v",
 ]
+# --use_fast_math only where the arithmetic is a softmax / activation inside a tensor-core kernel (ex2.approx, rcp.approx,
+# flush-to-zero are part of those kernels' design); the normalisation kernels (GroupNorm, LayerNorm: rsqrt / division feed
+# every output element) and the residual merge keep IEEE division / sqrt and denormals.
+FAST_MATH_SOURCES = {"gemm_pair_tcgen05.cu", "temporal_attn.cu", "cross_attn.cu", "temporal_block_fused.cu", "bias_act_residual.cu"}
 
 
 def _nvcc() -> str:
@@ -35,7 +39,7 @@ def sources():
 
 
 def _digest() -> str:
-    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    h = hashlib.sha256((" ".join(NVCC_FLAGS) + "|" + ",".join(sorted(FAST_MATH_SOURCES))).encode())
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for f in sorted(os.listdir(root)):
             if f.endswith((".cu", ".cuh", ".h")):
@@ -55,7 +59,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
-        r = subprocess.run([nvcc, *NVCC_FLAGS, "-c", src, "-o", obj], capture_output=True, text=True)
+        flags = NVCC_FLAGS + (["--use_fast_math"] if os.path.basename(src) in FAST_MATH_SOURCES else [])
+        r = subprocess.run([nvcc, *flags, "-c", src, "-o", obj], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
         with open(obj + ".log", "w") as fh:

@@ -544,15 +544,6 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
-int gemm_impl() {  // CA_GEMM_IMPL=1cta selects the single-CTA yardstick kernel
-  static int impl = -1;
-  if (impl < 0) {
-    const char* e = getenv("CA_GEMM_IMPL");
-    impl = (e && e[0] == '1') ? 1 : 2;
-  }
-  return impl;
-}
-
 // One way to tile the problem, and what the busiest pair's main loop is expected to cost with it.
 struct Plan {
   int bn = 0, nsub = 1, stages = 0, acc_stages = 2, num_n_blocks = 0;
@@ -602,7 +593,6 @@ extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, c
                                                                 long long ldx, long long ldr, long long ldy, int epilogue,
                                                                 int dtype, void* stream) {
   using namespace ca;
-  if (gemm_impl() == 1) return linear_1cta(x, w, bias, residual, y, m, n, k, ldx, ldr, ldy, epilogue, dtype, stream);
   CA_CHECK_ARG(x && w && y, "linear: null pointer");
   CA_CHECK_ARG(dtype == CA_BF16 || dtype == CA_F16, "linear: dtype must be bf16 or f16 (tcgen05 kind::f16)");
   CA_CHECK_ARG(m >= 0 && n > 0 && k > 0, "linear: bad sizes m=%lld n=%d k=%d", m, n, k);

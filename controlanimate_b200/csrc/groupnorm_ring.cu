@@ -5,7 +5,7 @@
 // Replaces InflatedGroupNorm.forward + F.silu (reference animatediff/models/resnet.py:23-31, 191-192,
 // 199-208; unet.py:614-615) and the per-frame transformer-entry GroupNorm (attention.py:131).
 //
-// Why a second design next to groupnorm_team.cu: the team kernel runs every CTA through
+// Why this design (round 1's persistent "team" kernel, since removed, ran every CTA through
 // load -> statistics -> team barrier -> normalise -> store for one band at a time, so the whole GPU moves
 // in lock-step and HBM idles during the statistics and the barrier (measured 28 % of the copy roofline at
 // c320 64x64, profiles/r01c_microbench_quick.json).  Here the tensor is cut into small SLICES (k*j rows of
@@ -26,11 +26,11 @@
 // domain can always complete: no deadlock as long as the grid is co-resident (cooperative launch).
 //
 // Shapes outside this path (domains larger than the ring can hold: the v1 GroupNorm over (f,h,w); fp32
-// storage; c % 8 != 0) fall through to groupnorm_team.cu / the split kernels in groupnorm_silu.cu.
+// storage; c % 8 != 0) fall through to the split kernels in groupnorm_silu.cu.
 #include <stdlib.h>
 
 #include "common.cuh"
-#include "groupnorm_team.cuh"
+#include "groupnorm_paths.cuh"
 #include "tma.cuh"
 
 namespace ca {

@@ -22,7 +22,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
-#include "groupnorm_team.cuh"
+#include "groupnorm_paths.cuh"
 
 namespace ca {
 namespace {
@@ -647,12 +647,8 @@ extern "C" __attribute__((visibility("default"))) size_t ca_groupnorm_workspace_
   ca::GnPlan pl;
   if (ca::make_plan(b, c, f, h, w, groups, per_frame, layout, dtype, &pl) != CA_OK) return 0;
   const size_t split = pl.partial_bytes + pl.counter_bytes + pl.final_bytes;
-  size_t team = layout == CA_LAYOUT_BFHWC ? ca::gn_team_workspace_bytes(b, c, f, h, w, groups, per_frame, dtype) : 0;
   const size_t ring = layout == CA_LAYOUT_BFHWC ? ca::gn_ring_workspace_bytes(b, c, f, h, w, groups, per_frame, dtype) : 0;
-  if (ring > team) team = ring;
-  const size_t strm = layout == CA_LAYOUT_BFHWC ? ca::gn_stream_workspace_bytes(b, c, f, h, w, groups, per_frame, dtype) : 0;
-  if (strm > team) team = strm;
-  return split > team ? split : team;
+  return split > ring ? split : ring;
 }
 
 extern "C" __attribute__((visibility("default"))) int ca_groupnorm_silu(const void* x, void* y, const float* gamma,
@@ -666,19 +662,12 @@ extern "C" __attribute__((visibility("default"))) int ca_groupnorm_silu(const vo
   int rc = make_plan(b, c, f, h, w, groups, per_frame, layout, dtype, &pl);
   if (rc != CA_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (layout == CA_LAYOUT_BFHWC) {  // native layout: small domains -> one CTA per (domain, group slab); else [opt-in streaming pair,] pipelined slice ring,
-    // else persistent team kernel
+  if (layout == CA_LAYOUT_BFHWC) {  // native layout: small domains -> one CTA per (domain, group slab); else the pipelined slice ring
     bool handled = false;
     rc = gn_slab_launch(x, y, gamma, beta, temb, temb_ld > 0 ? temb_ld : c, b, c, f, h, w, groups, eps, per_frame, apply_silu, dtype, st,
                         &handled);
     if (rc != CA_OK || handled) return rc;
-    rc = gn_stream_launch(x, y, gamma, beta, temb, temb_ld > 0 ? temb_ld : c, b, c, f, h, w, groups, eps, per_frame, apply_silu, dtype,
-                          workspace, workspace_bytes, st, &handled);
-    if (rc != CA_OK || handled) return rc;
     rc = gn_ring_launch(x, y, gamma, beta, temb, temb_ld > 0 ? temb_ld : c, b, c, f, h, w, groups, eps, per_frame, apply_silu, dtype, workspace,
-                        workspace_bytes, st, &handled);
-    if (rc != CA_OK || handled) return rc;
-    rc = gn_team_launch(x, y, gamma, beta, temb, temb_ld > 0 ? temb_ld : c, b, c, f, h, w, groups, eps, per_frame, apply_silu, dtype, workspace,
                         workspace_bytes, st, &handled);
     if (rc != CA_OK || handled) return rc;
   }

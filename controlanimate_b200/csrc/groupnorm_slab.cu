@@ -14,7 +14,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
-#include "groupnorm_team.cuh"
+#include "groupnorm_paths.cuh"
 #include "tma.cuh"
 
 namespace ca {

@@ -38,7 +38,7 @@ if __name__ == "__main__":
         sys.exit(0)
     base = run()
     print("config 4 forward ok:", tuple(base.shape), "rms", float(base.pow(2).mean().sqrt()))
-    for tag, env in (("gn ring/team instead of slab", {"CA_GN_SLAB": "0"}), ("gn split launches", {"CA_GN_SLAB": "0", "CA_GN_RING": "0", "CA_GN_TEAM": "0"}),
+    for tag, env in (("gn ring instead of slab", {"CA_GN_SLAB": "0"}), ("gn split launches", {"CA_GN_SLAB": "0", "CA_GN_RING": "0"}),
                      ("layernorm persistent", {"CA_LN_MODE": "persist"})):
         path = f"/tmp/config4_{abs(hash(tag))}.pt"
         subprocess.run([sys.executable, __file__, "child", path], env=dict(os.environ, **env), check=True)
