@@ -14,8 +14,9 @@ import sys
 
 FAMILIES = {  # bench.py family -> substrings of the kernel names that implement it
     "linear_tcgen05": ["gemm_pair_kernel", "gemm_kernel", "gemm_tcgen05"],
-    "groupnorm_silu": ["gn_ring_kernel", "gn_team_kernel", "gn_stream", "gn_bfhwc", "gn_ncfhw", "gn_finalize"],
-    "layernorm_pe": ["layernorm_ring_kernel", "layernorm_pe_kernel"],
+    "groupnorm_silu": ["gn_ring_kernel", "gn_slab_kernel", "gn_split", "gn_bfhwc", "gn_ncfhw", "gn_finalize"],
+    "layernorm_pe": ["layernorm_ring_kernel", "layernorm_pe_kernel", "layernorm_flat_kernel"],
+    "row_stats": ["row_stats_kernel"],
     "temporal_attn_core": ["temporal_attn_kernel"],
     "cross_attn_core": ["cross_attn_kernel"],
     "bias_act_residual": ["bias_act_residual_kernel"],

@@ -50,7 +50,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--out", default="gpurun_out/microbench.json")
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--only", default="", help="comma list of kernel families: gn,ln,attn,xattn,copy,gemm,merge")
+    ap.add_argument("--only", default="", help="comma list of kernel families: gn,ln,attn,xattn,fused,copy,gemm,merge")
     args = ap.parse_args()
     only = set(filter(None, args.only.split(",")))
     want = lambda fam: not only or fam in only  # noqa: E731
@@ -127,6 +127,23 @@ def main():
                 vh = kvx[:, :, c:].reshape(b, 77, 8, c // 8).transpose(1, 2).repeat_interleave(f, dim=0)
                 us, mn = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qh, kh, vh), args.iters, flush)
                 add("torch_sdpa(yardstick)", f"frames{b * f} d{s * s} c{c} (hd {c // 8}) L77", us, mn, 2.0 * T * c * 2, 4.0 * 77 * c * T)
+            if c in ops.FUSED_TEMPORAL_WIDTHS and want("fused"):
+                # the whole temporal-attention block in one launch vs the four launches it replaces
+                wq_, wk_, wv_, wo_ = (torch.randn(c, c, device=dev, dtype=bt) * c ** -0.5 for _ in range(4))
+                perm = ops.pack_qkv_per_head(wq_, wk_, wv_, 8)
+                w3_ = torch.cat([wq_, wk_, wv_]).contiguous()
+                flops = T * (8.0 * c * c + 4.0 * f * c)
+                us, mn = timeit(lambda: ops.temporal_attention_fused(tok, g, be, pe, perm, wo_, be, batch=b, frames=f, sites=s * s, heads=8,
+                                                                     out=yt), args.iters, flush)
+                add("temporal_attn_fused", f"b{b} f{f} d{s * s} c{c}", us, mn, 2.0 * T * c * 2 + 8.0 * c * c, flops, tensor=True)
+
+                def four():
+                    n_ = ops.layernorm_pe(tok, g, be, 1e-5, pe=pe, frames=f, sites=s * s)
+                    qkv_ = ops.linear(n_, w3_)
+                    o_ = ops.temporal_attention_core(qkv_[:, :c], qkv_[:, c:2 * c], qkv_[:, 2 * c:], batch=b, frames=f, sites=s * s, heads=8)
+                    return ops.linear(o_, wo_, be, residual=tok)
+                us, mn = timeit(four, args.iters, flush)
+                add("temporal_attn_4launch", f"b{b} f{f} d{s * s} c{c}", us, mn, 2.0 * T * c * 2 + 8.0 * c * c, flops, tensor=True)
             if f == 16 and want("gemm"):
                 # the motion module's GEMMs: fused QKV, out-proj + residual, GEGLU, FF out
                 w3 = torch.randn(3 * c, c, device=dev, dtype=bt) * c ** -0.5
@@ -149,6 +166,20 @@ def main():
                     w_ = {"proj_in": w1, "qkv": w3, "out+bias+res": w1, "geglu": wg, "ff_out+res": w2}[nm]
                     us_c, mn_c = timeit(lambda: torch.nn.functional.linear(a_, w_), args.iters, flush)
                     add("cublas_linear(yardstick)", f"{nm} m{m_} n{n_} k{k_}", us_c, mn_c, nb, 2.0 * m_ * n_ * k_, tensor=True)
+                    # the same arithmetic the fused kernel does, on cuBLAS + torch elementwise ops
+                    bb = bias[:w_.shape[0]].to(bt)
+                    if nm == "geglu":
+                        def cub_epi():
+                            av, gv = torch.nn.functional.linear(a_, w_, bb).chunk(2, dim=-1)
+                            return av * torch.nn.functional.gelu(gv)
+                    elif "res" in nm:
+                        def cub_epi():
+                            return torch.addmm(yt, a_, w_.t()).add_(bb)
+                    else:
+                        def cub_epi():
+                            return torch.nn.functional.linear(a_, w_, bb)
+                    us_e, mn_e = timeit(cub_epi, args.iters, flush)
+                    add("cublas+epilogue(yardstick)", f"{nm} m{m_} n{n_} k{k_}", us_e, mn_e, nb, 2.0 * m_ * n_ * k_, tensor=True)
             del x, xn, tok, qkv, o, yt
             torch.cuda.empty_cache()
 

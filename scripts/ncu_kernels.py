@@ -13,7 +13,7 @@ which = sys.argv[1] if len(sys.argv) > 1 else "all"
 L.load(build_if_missing=False)
 dev, bt = torch.device("cuda"), torch.bfloat16
 b, f = 2, 16
-levels = [(320, 64), (1280, 16)]
+levels = [(320, 64), (640, 32), (1280, 16)]
 flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
 for _ in range(3):
     for c, s in levels:
@@ -36,6 +36,10 @@ for _ in range(3):
             qx = torch.randn(T, c, device=dev, dtype=bt)
             kvx = torch.randn(b, 77, 2 * c, device=dev, dtype=bt)
             ops.cross_attention_core(qx, kvx[:, :, :c], kvx[:, :, c:], frames=b * f, sites=s * s, heads=8)
+        if which in ("all", "fused") and c == 320:
+            wq = torch.randn(c, c, device=dev, dtype=bt) * c ** -0.5
+            perm = ops.pack_qkv_per_head(wq, wq, wq, 8)
+            ops.temporal_attention_fused(tok, g, be, torch.randn(32, c, device=dev), perm, wq, be, batch=b, frames=f, sites=s * s, heads=8)
         if which in ("all", "gemm"):
             w3 = torch.randn(3 * c, c, device=dev, dtype=bt)
             w1 = torch.randn(c, c, device=dev, dtype=bt)
