@@ -311,6 +311,7 @@ def run_b200(args):
     unet = utils.build_on_device(lambda: un.UNet3DConditionModel(**cfg), dev, dtype, seed=1)
     nets = [utils.build_on_device(lambda: un.ControlNetModel(), dev, dtype, seed=2 + k) for k in range(n_nets)]
     mc = pipeline.MultiControlNetResiduals(nets, cond_scale)
+    mc.overlap = bool(args.stream_overlap) and not args.no_graph
     sched = pipeline.DDIMScheduler()
     timesteps = sched.set_timesteps(n_steps)
     step_par = parallel.StepParallel(mode, rank, world, n_nets=n_nets) if mode in parallel.StepParallel.MODES else None
@@ -452,6 +453,7 @@ def run_b200(args):
             # replay = launches recorded in one captured step x timed steps)
             "gpu_launches": launches if launches else kern["launches_per_step"] * args.steps,
             "cuda_graph": not args.no_graph,
+            "controlnet_streams": n_nets if mc.overlap else 0,
             "roofline": top,
             "kernels": kern["families"],
             "own_kernel_share_of_step": kern["own_share"],
@@ -500,6 +502,8 @@ def main():
                     help="how N > 1 GPUs are used (see the module docstring)")
     ap.add_argument("--no-eager-yardstick", dest="eager_yardstick", action="store_false",
                     help="skip the torch bf16 eager yardstick (the reference's op sequence under stock PyTorch on the same GPU)")
+    ap.add_argument("--stream-overlap", type=int, default=int(os.environ.get("CA_STREAM_OVERLAP", "0")),
+                    help="1: every ControlNet on its own CUDA stream next to the UNet encoder (inside the captured graph)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--torch-profile", default="", help="write a torch.profiler op table of one eager step to this path")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")

@@ -58,7 +58,9 @@ constexpr int kMaxStages = 12;
 constexpr int kMaxSlots = 4;    // staging slots per epilogue warp: 4 with a residual (TMA-prefetched two boxes ahead), else 2
 constexpr int kSlotBytes = 2048;  // one 32 x 32 box of 16-bit elements (SWIZZLE_64B)
 constexpr uint32_t kABytes = BM * BK * 2;
-enum { EPI_BIAS = 0, EPI_RES = 1, EPI_GEGLU = 2 };
+// EPI_LN / EPI_LN_GEGLU: x is the RAW input of a LayerNorm whose gain is folded into w; the epilogue applies the row's
+// (mean, rstd):  y = rstd * (acc - mean * colsum[n]) + shift[frame(row)][n]   (see ca_linear_ln)
+enum { EPI_BIAS = 0, EPI_RES = 1, EPI_GEGLU = 2, EPI_LN = 3, EPI_LN_GEGLU = 4 };
 
 struct PairParams {
   long long m;
@@ -69,7 +71,10 @@ struct PairParams {
   int num_m_blocks, num_n_blocks, num_k_blocks, stages;  // m blocks of 256 rows
   int acc_stages;  // TMEM accumulator stages: 2 when nsub * bn <= 256, else 1
   long long tiles;
-  const float* bias;
+  const float* bias;  // [n]; with a folded LayerNorm: the shift table [ln_shift_rows][n]
+  const float2* ln_stats;   // (mean, rstd) per row of x (folded LayerNorm), else null
+  const float* ln_colsum;   // sum_k w[n][k] per output column (of the gain-folded weights)
+  int ln_sites, ln_frames, ln_shift_rows;  // shift row of token row r: (r / ln_sites) % ln_frames (row 0 if the table has one row)
   void* y;
   const void* res;
   long long ldy, ldr;
@@ -251,6 +256,8 @@ template <typename T, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                      const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_r, const PairParams p) {
+  constexpr bool kGeglu = EPI == EPI_GEGLU || EPI == EPI_LN_GEGLU;
+  constexpr bool kLn = EPI == EPI_LN || EPI == EPI_LN_GEGLU;
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tmem_full[2], tmem_empty[2];
   __shared__ uint64_t res_full[kEpiWarps][kMaxSlots];
@@ -300,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     // rows of w this CTA supplies for sub-tile j of n-block nb: its half of the sub-tile's columns, or (GEGLU) the value
     // rows (rank 0) / gate rows (rank 1) of the n-block
     auto b_row = [&](int nb, int j) {
-      return EPI == EPI_GEGLU ? (int)rank * (p.n / 2) + nb * half : (nb * p.nsub + j) * p.bn + (int)rank * half;
+      return kGeglu ? (int)rank * (p.n / 2) + nb * half : (nb * p.nsub + j) * p.bn + (int)rank * half;
     };
     const uint32_t stage_tx = kABytes + (uint32_t)p.nsub * p.b_bytes;
     int stage = 0;
@@ -431,6 +438,37 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     uint32_t slot = 0, slot_phase = 0;
     long long it = 0;
+    // folded LayerNorm: (mean, rstd) of this lane's row, fetched one tile ahead (a cold 8-byte read per row and tile)
+    auto load_stats = [&](const TileWalk& tw) {
+      const long long r = (long long)tw.mb() * 2 * BM + (int)rank * BM + q * 32 + lane;
+      return (tw.valid() && r < p.m) ? __ldg(p.ln_stats + r) : make_float2(0.f, 0.f);
+    };
+    float2 st_next = make_float2(0.f, 0.f);
+    // ... and the per-column parameters of the NEXT box: lane j fetches column j's (colsum, shift) [GEGLU: value and gate
+    // column] one box ahead, so the L2 round trip of the table rows (they do not stay in the small L1 next to 200 KB of
+    // shared memory) is off the box's critical path; at the box they are broadcast through the staging slot.
+    auto shift_row = [&](const TileWalk& tw) {
+      const int r0 = tw.mb() * 2 * BM + (int)rank * BM + q * 32;
+      return p.ln_shift_rows > 1 ? p.bias + (size_t)((r0 / p.ln_sites) % p.ln_frames) * (size_t)p.n : p.bias;
+    };
+    auto load_prm = [&](const TileWalk& tw, int box_i) {
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!tw.valid() || my_n == 0) return r;
+      const int col = tw.nb() * p.out_cols + (part + box_i * kEpiParts) * 32 + lane;
+      const float* sh_row = shift_row(tw);
+      r.x = __ldg(p.ln_colsum + col);
+      r.y = __ldg(sh_row + col);
+      if constexpr (kGeglu) {
+        r.z = __ldg(p.ln_colsum + p.n / 2 + col);
+        r.w = __ldg(sh_row + p.n / 2 + col);
+      }
+      return r;
+    };
+    float4 prm_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (kLn) {
+      st_next = load_stats(TileWalk(p, pair, pairs));
+      prm_next = load_prm(TileWalk(p, pair, pairs), 0);
+    }
     for (TileWalk w(p, pair, pairs); w.valid(); w.next(), ++it) {
       const int acc = p.acc_stages == 2 ? (int)(it & 1) : 0;
       const uint32_t acc_par = p.acc_stages == 2 ? (uint32_t)((it >> 1) & 1) : (uint32_t)(it & 1);
@@ -442,6 +480,17 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (my_n == 0 || p.dbg == 1) {
         release_acc(acc);
         continue;
+      }
+      // folded LayerNorm: this lane's row statistics and the warp's shift row (32 | ln_sites: one frame per warp)
+      f2 ln_rs = splat(1.f), ln_nm = splat(0.f);
+      const float* bias = p.bias;
+      TileWalk ahead = w;
+      if constexpr (kLn) {
+        const float2 st = st_next;
+        ahead.next();
+        st_next = load_stats(ahead);
+        ln_rs = splat(st.y);
+        ln_nm = splat(-st.x * st.y);
       }
       // one box per iteration, NOT unrolled: the hot loops have to stay inside the instruction cache (round 1's fully
       // unrolled epilogue was 46 KB of SASS)
@@ -462,39 +511,89 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         __syncwarp();
         f2 v[16];
-        if constexpr (EPI == EPI_GEGLU) {
+        if constexpr (kGeglu) {
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
             uint32_t a[16], g[16];
             tmem_ld16(taddr + (uint32_t)(bc + 16 * h2), a);
             tmem_ld16(taddr + (uint32_t)(half + bc + 16 * h2), g);
+            // per-column parameters: fetched while the TMEM reads are in flight
+            const int gc = col0 + bc + 16 * h2;
+            f2 sa[8], sg[8];
+            if constexpr (kLn) {
+              if (h2 == 0) {  // broadcast the box's prefetched (colsum, shift) pairs through the (still unused) staging slot
+                const float4 prm = prm_next;
+                prm_next = i + 1 < my_n ? load_prm(w, i + 1) : load_prm(ahead, 0);
+                float* sc = reinterpret_cast<float*>(buf);
+                sc[(lane >> 1) * 4 + (lane & 1)] = prm.x;
+                sc[(lane >> 1) * 4 + 2 + (lane & 1)] = prm.y;
+                sc[64 + (lane >> 1) * 4 + (lane & 1)] = prm.z;
+                sc[64 + (lane >> 1) * 4 + 2 + (lane & 1)] = prm.w;
+                __syncwarp();
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 ca = *reinterpret_cast<const float4*>(buf + (8 * h2 + j) * 16);
+                const float4 cg = *reinterpret_cast<const float4*>(buf + 256 + (8 * h2 + j) * 16);
+                sa[j] = fma2(ln_nm, pk(ca.x, ca.y), pk(ca.z, ca.w));
+                sg[j] = fma2(ln_nm, pk(cg.x, cg.y), pk(cg.z, cg.w));
+              }
+              if (h2 == 1) __syncwarp();  // every lane has read the parameters before the output box overwrites them
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+                if (bias) {
+                  ba = __ldg(reinterpret_cast<const float4*>(bias + gc + j));
+                  bg = __ldg(reinterpret_cast<const float4*>(bias + p.n / 2 + gc + j));
+                }
+                sa[j / 2] = pk(ba.x, ba.y);
+                sa[j / 2 + 1] = pk(ba.z, ba.w);
+                sg[j / 2] = pk(bg.x, bg.y);
+                sg[j / 2 + 1] = pk(bg.z, bg.w);
+              }
+            }
             tmem_ld_wait();
             if (h2 == 1 && i == my_n - 1) release_acc(acc);
-            const int gc = col0 + bc + 16 * h2;
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
-              if (p.bias) {
-                ba = __ldg(reinterpret_cast<const float4*>(p.bias + gc + j));
-                bg = __ldg(reinterpret_cast<const float4*>(p.bias + p.n / 2 + gc + j));
-              }
-              v[8 * h2 + j / 2] = geglu2(add2(pk(__uint_as_float(a[j]), __uint_as_float(a[j + 1])), pk(ba.x, ba.y)),
-                                         add2(pk(__uint_as_float(g[j]), __uint_as_float(g[j + 1])), pk(bg.x, bg.y)));
-              v[8 * h2 + j / 2 + 1] = geglu2(add2(pk(__uint_as_float(a[j + 2]), __uint_as_float(a[j + 3])), pk(ba.z, ba.w)),
-                                             add2(pk(__uint_as_float(g[j + 2]), __uint_as_float(g[j + 3])), pk(bg.z, bg.w)));
+            for (int j = 0; j < 16; j += 2) {
+              const f2 av = pk(__uint_as_float(a[j]), __uint_as_float(a[j + 1])), gv = pk(__uint_as_float(g[j]), __uint_as_float(g[j + 1]));
+              v[8 * h2 + j / 2] = kLn ? geglu2(fma2(ln_rs, av, sa[j / 2]), fma2(ln_rs, gv, sg[j / 2])) : geglu2(add2(av, sa[j / 2]), add2(gv, sg[j / 2]));
             }
           }
         } else {
           uint32_t a[32];
           tmem_ld32(taddr + (uint32_t)bc, a);
+          // the per-column parameters do not depend on the accumulator: fetch them while the TMEM read is in flight
+          f2 sh[16];
+          if constexpr (kLn) {
+            const float4 prm = prm_next;
+            prm_next = i + 1 < my_n ? load_prm(w, i + 1) : load_prm(ahead, 0);
+            float* sc = reinterpret_cast<float*>(buf);
+            sc[(lane >> 1) * 4 + (lane & 1)] = prm.x;
+            sc[(lane >> 1) * 4 + 2 + (lane & 1)] = prm.y;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float4 cs = *reinterpret_cast<const float4*>(buf + j * 16);
+              sh[j] = fma2(ln_nm, pk(cs.x, cs.y), pk(cs.z, cs.w));
+            }
+            __syncwarp();  // every lane has read the parameters before the output box overwrites them
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 ba = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (bias) ba = __ldg(reinterpret_cast<const float4*>(bias + col0 + bc + j));
+              sh[j / 2] = pk(ba.x, ba.y);
+              sh[j / 2 + 1] = pk(ba.z, ba.w);
+            }
+          }
           tmem_ld_wait();
           if (i == my_n - 1) release_acc(acc);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 ba = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) ba = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + bc + j));
-            v[j / 2] = add2(pk(__uint_as_float(a[j]), __uint_as_float(a[j + 1])), pk(ba.x, ba.y));
-            v[j / 2 + 1] = add2(pk(__uint_as_float(a[j + 2]), __uint_as_float(a[j + 3])), pk(ba.z, ba.w));
+          for (int j = 0; j < 32; j += 2) {
+            const f2 av = pk(__uint_as_float(a[j]), __uint_as_float(a[j + 1]));
+            v[j / 2] = kLn ? fma2(ln_rs, av, sh[j / 2]) : add2(av, sh[j / 2]);
           }
         }
         if constexpr (EPI == EPI_RES) {
@@ -585,14 +684,15 @@ bool make_plan(Plan& pl, int bn, int nsub, int n, int k, long long m, bool geglu
   return true;
 }
 
-}  // namespace
-}  // namespace ca
+// a LayerNorm folded into the projection that consumes it (ca_linear_ln)
+struct LnFold {
+  const float2* stats;
+  const float* colsum;
+  int sites, frames, shift_rows;
+};
 
-extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, const void* w, const float* bias,
-                                                                const void* residual, void* y, long long m, int n, int k,
-                                                                long long ldx, long long ldr, long long ldy, int epilogue,
-                                                                int dtype, void* stream) {
-  using namespace ca;
+int linear_impl(const void* x, const void* w, const float* bias, const void* residual, void* y, long long m, int n, int k,
+                long long ldx, long long ldr, long long ldy, int epilogue, int dtype, void* stream, const LnFold* ln) {
   CA_CHECK_ARG(x && w && y, "linear: null pointer");
   CA_CHECK_ARG(dtype == CA_BF16 || dtype == CA_F16, "linear: dtype must be bf16 or f16 (tcgen05 kind::f16)");
   CA_CHECK_ARG(m >= 0 && n > 0 && k > 0, "linear: bad sizes m=%lld n=%d k=%d", m, n, k);
@@ -637,6 +737,10 @@ extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, c
   p.num_n_blocks = best.num_n_blocks;
   p.tiles = (long long)p.num_m_blocks * p.num_n_blocks;
   p.bias = bias; p.y = y; p.ldy = ldy; p.res = residual; p.ldr = ldr;
+  if (ln) {
+    p.ln_stats = ln->stats; p.ln_colsum = ln->colsum;
+    p.ln_sites = ln->sites; p.ln_frames = ln->frames; p.ln_shift_rows = ln->shift_rows;
+  }
   p.slots = residual ? kMaxSlots : 2;
   p.b_bytes = (uint32_t)(p.bn / 2) * BK * 2;
   p.stage_bytes = (uint32_t)best.stage_bytes;
@@ -711,13 +815,42 @@ extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, c
     }
     return CA_OK;
   };
-  const int epi = geglu ? EPI_GEGLU : (residual ? EPI_RES : EPI_BIAS);
+  const int epi = ln ? (geglu ? EPI_LN_GEGLU : EPI_LN) : geglu ? EPI_GEGLU : (residual ? EPI_RES : EPI_BIAS);
   if (dtype == CA_BF16) {
+    if (epi == EPI_LN_GEGLU) return run(gemm_pair_kernel<__nv_bfloat16, EPI_LN_GEGLU>);
+    if (epi == EPI_LN) return run(gemm_pair_kernel<__nv_bfloat16, EPI_LN>);
     if (epi == EPI_GEGLU) return run(gemm_pair_kernel<__nv_bfloat16, EPI_GEGLU>);
     if (epi == EPI_RES) return run(gemm_pair_kernel<__nv_bfloat16, EPI_RES>);
     return run(gemm_pair_kernel<__nv_bfloat16, EPI_BIAS>);
   }
+  if (epi == EPI_LN_GEGLU) return run(gemm_pair_kernel<__half, EPI_LN_GEGLU>);
+  if (epi == EPI_LN) return run(gemm_pair_kernel<__half, EPI_LN>);
   if (epi == EPI_GEGLU) return run(gemm_pair_kernel<__half, EPI_GEGLU>);
   if (epi == EPI_RES) return run(gemm_pair_kernel<__half, EPI_RES>);
   return run(gemm_pair_kernel<__half, EPI_BIAS>);
+}
+
+}  // namespace
+}  // namespace ca
+
+extern "C" __attribute__((visibility("default"))) int ca_linear(const void* x, const void* w, const float* bias,
+                                                                const void* residual, void* y, long long m, int n, int k,
+                                                                long long ldx, long long ldr, long long ldy, int epilogue,
+                                                                int dtype, void* stream) {
+  return ca::linear_impl(x, w, bias, residual, y, m, n, k, ldx, ldr, ldy, epilogue, dtype, stream, nullptr);
+}
+
+extern "C" __attribute__((visibility("default"))) int ca_linear_ln(const void* x, const void* w_gain, const float* colsum,
+                                                                   const float* shift, int shift_rows, int frames, int sites,
+                                                                   const float* stats, void* y, long long m, int n, int k,
+                                                                   long long ldx, long long ldy, int epilogue, int dtype,
+                                                                   void* stream) {
+  using namespace ca;
+  CA_CHECK_ARG(colsum && shift && stats, "linear_ln: null pointer");
+  CA_CHECK_ARG(shift_rows == 1 || (frames >= 1 && shift_rows >= frames && sites >= 32 && sites % 32 == 0),
+               "linear_ln: a per-frame shift table needs frames <= shift_rows and sites %% 32 == 0 (got frames=%d rows=%d sites=%d)",
+               frames, shift_rows, sites);
+  CA_CHECK_ARG((reinterpret_cast<uintptr_t>(stats) & 7) == 0 && aligned16(colsum) && aligned16(shift), "linear_ln: misaligned tables");
+  LnFold ln{reinterpret_cast<const float2*>(stats), colsum, sites < 1 ? 1 : sites, frames < 1 ? 1 : frames, shift_rows};
+  return linear_impl(x, w_gain, shift, nullptr, y, m, n, k, ldx, ldy, ldy, epilogue, dtype, stream, &ln);
 }

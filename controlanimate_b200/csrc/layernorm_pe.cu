@@ -419,6 +419,107 @@ __global__ void __launch_bounds__((kLnRingWarps + 1) * 32, 2) layernorm_ring_ker
   }
 }
 
+
+// Row statistics only: (mean, rstd) of every row, the arithmetic of layernorm_flat_kernel's first two passes (exact two-pass
+// variance from the register-resident row).  Feeds ca_linear_ln, which applies the normalisation in the epilogue of the
+// projection that consumes the LayerNorm — the normalised tensor is never written.
+template <typename T, int LPR, int NV>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
+    row_stats_kernel(const T* __restrict__ x, float2* __restrict__ stats, long long rows, int c, long long ldx, float eps) {
+  constexpr int VEC = 8;
+  constexpr int R = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, sl = lane % LPR;
+  const int nvec = c / VEC;
+  const long long row = ((long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * R + sub;
+  const bool live = row < rows;
+  const float inv_c = 1.0f / (float)c;
+  uint4 raw[NV];
+  const T* xr = x + row * ldx;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = sl + i * LPR;
+    raw[i] = (live && vi < nvec) ? ldg_keep(xr + vi * VEC) : make_uint4(0u, 0u, 0u, 0u);  // the projection re-reads x: keep it in L2
+  }
+  float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float2 v[4];
+    unpack2(raw[i].x, v[0].x, v[0].y, T());
+    unpack2(raw[i].y, v[1].x, v[1].y, T());
+    unpack2(raw[i].z, v[2].x, v[2].y, T());
+    unpack2(raw[i].w, v[3].x, v[3].y, T());
+    sum2 = __fadd2_rn(sum2, __fadd2_rn(__fadd2_rn(v[0], v[1]), __fadd2_rn(v[2], v[3])));
+  }
+  float sum = sum2.x + sum2.y;
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * inv_c;
+  const float2 nmean = make_float2(-mean, -mean);
+  float2 sq2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (sl + i * LPR < nvec) {
+      float2 v[4];
+      unpack2(raw[i].x, v[0].x, v[0].y, T());
+      unpack2(raw[i].y, v[1].x, v[1].y, T());
+      unpack2(raw[i].z, v[2].x, v[2].y, T());
+      unpack2(raw[i].w, v[3].x, v[3].y, T());
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 dl = __fadd2_rn(v[j], nmean);
+        sq2 = __ffma2_rn(dl, dl, sq2);
+      }
+    }
+  }
+  float sq = sq2.x + sq2.y;
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if (live && sl == 0) stats[row] = make_float2(mean, rsqrtf(sq * inv_c + eps));
+}
+
+}  // namespace
+}  // namespace ca
+
+extern "C" __attribute__((visibility("default"))) int ca_row_stats(const void* x, float* stats, long long rows, int c,
+                                                                   long long ldx, float eps, int dtype, void* stream) {
+  using namespace ca;
+  CA_CHECK_ARG(x && stats, "row_stats: null pointer");
+  CA_CHECK_ARG(dtype == CA_BF16 || dtype == CA_F16, "row_stats: dtype must be bf16 or f16");
+  CA_CHECK_ARG(rows >= 0 && c > 0 && c % 8 == 0 && ldx >= c && ldx % 8 == 0, "row_stats: bad sizes rows=%lld c=%d ldx=%lld", rows, c, ldx);
+  CA_CHECK_ARG(aligned16(x) && (reinterpret_cast<uintptr_t>(stats) & 7) == 0, "row_stats: misaligned pointer");
+  if (rows == 0) return CA_OK;
+  const int nvec = c / 8;
+  int lpr = 8;
+  while (lpr < 32 && (nvec + lpr - 1) / lpr > 5) lpr <<= 1;
+  const int nv = (nvec + lpr - 1) / lpr;
+  CA_CHECK_ARG(nv <= 5, "row_stats: c=%d too wide (<= 1280)", c);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int rows_per_cta = kWarpsPerCta * (32 / lpr);
+  const long long grid = (rows + rows_per_cta - 1) / rows_per_cta;
+  CA_CHECK_ARG(grid < (1ll << 31), "row_stats: too many rows");
+  const int rc = dispatch_dtype(dtype, [&](auto tag) -> int {
+    using T = decltype(tag);
+    if constexpr (sizeof(T) == 2) {
+      auto run = [&](auto kernel) -> int {
+        kernel<<<(unsigned)grid, kWarpsPerCta * 32, 0, st>>>(reinterpret_cast<const T*>(x), reinterpret_cast<float2*>(stats), rows, c, ldx, eps);
+        return CA_OK;
+      };
+#define CA_RS_CASE(L_, N_) if (lpr == L_ && nv <= N_) return run(row_stats_kernel<T, L_, N_>)
+      CA_RS_CASE(8, 1); CA_RS_CASE(8, 2); CA_RS_CASE(8, 3); CA_RS_CASE(8, 5);
+      CA_RS_CASE(16, 3); CA_RS_CASE(16, 5);
+      CA_RS_CASE(32, 3); CA_RS_CASE(32, 5);
+#undef CA_RS_CASE
+    }
+    return CA_ERR_UNSUPPORTED;
+  });
+  if (rc != CA_OK) return rc;
+  CA_CUDA(cudaGetLastError());
+  return CA_OK;
+}
+
+namespace ca {
+namespace {
 }  // namespace
 }  // namespace ca
 

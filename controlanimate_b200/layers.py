@@ -15,7 +15,7 @@ boundaries B2/B4) and return the layout they were given.
 from __future__ import annotations
 
 import math
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 import torch.nn as nn
@@ -186,7 +186,37 @@ class _FusedWeights:
         return self._w
 
 
+class _LnFold:
+    """A LayerNorm folded into the projection(s) behind it (ops.fold_layernorm): gain-scaled weights, their column sums
+    and the shift table, rebuilt when any source tensor changes."""
+
+    def __init__(self):
+        self._key = None
+        self._val = None
+
+    def get(self, ws: Sequence[torch.Tensor], norm: nn.LayerNorm, bias: Optional[torch.Tensor] = None,
+            pe: Optional[torch.Tensor] = None):
+        srcs = list(ws) + [norm.weight, norm.bias] + [t for t in (bias, pe) if t is not None]
+        key = tuple((t._version, t.data_ptr(), t.dtype, t.device) for t in srcs)
+        if key != self._key:
+            w = ws[0].detach() if len(ws) == 1 else torch.cat([w.detach() for w in ws], dim=0)
+            self._val = ops.fold_layernorm(w, norm.weight, norm.bias, bias=bias, pe=pe)
+            self._key = key
+        return self._val
+
+
+def ln_foldable(h: torch.Tensor, sites: int = 32) -> bool:
+    """CA_LN_FOLD=1: LayerNorm -> projection pairs run as row statistics + one GEMM whose epilogue normalises (ca_row_stats /
+    ca_linear_ln) instead of ca_layernorm_pe + ca_linear.  Parity-green, but measured a wash (profiles/r02_notes.md §2: the
+    step gains 0.5 ms of 72 while the projection GEMMs, now carrying the normalisation, drop from 0.69 to 0.66 of the
+    tensor roofline), so the two-launch form stays the default."""
+    return _LN_FOLD and h.dtype in (torch.bfloat16, torch.float16) and h.shape[-1] % 32 == 0 and h.shape[-1] <= 1280 \
+        and sites % 32 == 0
+
+
 import os as _os
+
+_LN_FOLD = _os.environ.get("CA_LN_FOLD", "0") == "1"
 
 # CA_FUSED_TEMPORAL=1 routes the temporal-attention blocks of the 320-wide level through the one-launch kernel
 # (ca_temporal_attn_fused).  It is parity-green but, as measured in profiles/r02_fused_notes.md, still slower than the
@@ -338,9 +368,25 @@ class TemporalAttention(nn.Module):
             return o.reshape(b, d, f, c).permute(0, 2, 1, 3).reshape(b * f * d, c) + residual
         wqkv = self._qkv.get(self.to_q.weight, self.to_k.weight, self.to_v.weight)
         qkv = ops.linear(n_tok, wqkv)
+        return self._attend(qkv, residual, b, f, d)
+
+    def _attend(self, qkv: torch.Tensor, residual: torch.Tensor, b: int, f: int, d: int) -> torch.Tensor:
+        c = residual.shape[-1]
         o = ops.temporal_attention_core(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], batch=b, frames=f, sites=d,
                                         heads=self.heads, scale=self.scale)
         return ops.linear(o, self.to_out[0].weight, f32(self.to_out[0].bias), residual=residual)
+
+    def native_ln(self, h: torch.Tensor, norm: nn.LayerNorm, b: int, f: int, d: int) -> torch.Tensor:
+        """h + to_out(attn(qkv(LayerNorm(h) + pe))) from the raw rows h: the LayerNorm (+PE) is applied by the QKV GEMM's
+        epilogue (motion_module.py:214-215, 285-288 folded into :321's projections)."""
+        pe = self.pos_encoder.pe if self.pos_encoder is not None else None
+        if pe is not None and pe.shape[-2] < f:
+            raise ValueError(f"video has {f} frames but the positional encoding only {pe.shape[-2]} (motion_module.py:236)")
+        if "_ln" not in self.__dict__:
+            self.__dict__["_ln"] = _LnFold()
+        w_gain, colsum, shift = self.__dict__["_ln"].get((self.to_q.weight, self.to_k.weight, self.to_v.weight), norm, pe=pe)
+        qkv = ops.linear_ln(h, ops.row_stats(h, norm.eps), w_gain, colsum, shift, frames=f, sites=d)
+        return self._attend(qkv, h, b, f, d)
 
 
 class _GEGLU(nn.Module):
@@ -360,6 +406,14 @@ class FeedForward(nn.Module):
         u = ops.linear(n_tok, self.net[0].proj.weight, f32(self.net[0].proj.bias), geglu=True)
         return ops.linear(u, self.net[2].weight, f32(self.net[2].bias), residual=residual)
 
+    def native_ln(self, h: torch.Tensor, norm: nn.LayerNorm) -> torch.Tensor:
+        """h + net.2(GEGLU(net.0.proj(LayerNorm(h)))) from the raw rows: the LayerNorm is applied in the GEGLU GEMM's epilogue."""
+        if "_ln" not in self.__dict__:
+            self.__dict__["_ln"] = _LnFold()
+        w_gain, colsum, shift = self.__dict__["_ln"].get((self.net[0].proj.weight,), norm, bias=self.net[0].proj.bias)
+        u = ops.linear_ln(h, ops.row_stats(h, norm.eps), w_gain, colsum, shift, geglu=True)
+        return ops.linear(u, self.net[2].weight, f32(self.net[2].bias), residual=h)
+
 
 class _TemporalTransformerBlock(nn.Module):
     def __init__(self, dim, heads, n_attn, max_len):
@@ -374,9 +428,14 @@ class _TemporalTransformerBlock(nn.Module):
             if attn.fused_ok(h, f):                                          # kernel (1) fused: one launch per attention block
                 h = attn.fused(h, norm, b, f, d)
                 continue
+            if ln_foldable(h, d) and isinstance(attn.processor, B200TemporalAttnProcessor):
+                h = attn.native_ln(h, norm, b, f, d)
+                continue
             pe = attn.pos_encoder.pe if attn.pos_encoder is not None else None
             n = ops.layernorm_pe(h, f32(norm.weight), f32(norm.bias), norm.eps, pe=f32(pe), frames=f, sites=d)
             h = attn.native(n, h, b, f, d)
+        if ln_foldable(h):
+            return self.ff.native_ln(h, self.ff_norm)                        # :221
         n = ops.layernorm_pe(h, f32(self.ff_norm.weight), f32(self.ff_norm.bias), self.ff_norm.eps)
         return self.ff.native(n, h)                                          # :221
 
@@ -594,15 +653,26 @@ class _SpatialAttention(nn.Module):
     def get_processor(self, return_deprecated_lora: bool = False):
         return self.processor
 
-    def native(self, n_tok, residual, n_frames, d, ctx=None, ctx_map=None):
+    def _project(self, n_tok, ws, norm):
+        """The input projection(s) of this attention: from LayerNorm'd tokens (norm None), or from the raw rows with the
+        LayerNorm `norm` folded into the GEMM (attention.py:271-286's norm1 / norm2 + to_q[/to_k/to_v])."""
+        if norm is None:
+            return ops.linear(n_tok, ws[0] if len(ws) == 1 else self._fused.get(*ws))
+        if "_ln" not in self.__dict__:
+            self.__dict__["_ln"] = _LnFold()
+        w_gain, colsum, shift = self.__dict__["_ln"].get(ws, norm)
+        return ops.linear_ln(n_tok, ops.row_stats(n_tok, norm.eps), w_gain, colsum, shift)
+
+    def native(self, n_tok, residual, n_frames, d, ctx=None, ctx_map=None, norm=None):
+        """`norm` given: n_tok are the RAW rows and the LayerNorm rides in the projection's epilogue."""
         c = n_tok.shape[-1]
         hd = c // self.heads
         if not self.is_cross:
-            qkv = ops.linear(n_tok, self._fused.get(self.to_q.weight, self.to_k.weight, self.to_v.weight))
+            qkv = self._project(n_tok, (self.to_q.weight, self.to_k.weight, self.to_v.weight), norm)
             qkv = qkv.reshape(n_frames, d, 3, self.heads, hd)
             q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))
         else:
-            q_tok = ops.linear(n_tok, self.to_q.weight)                                      # [T, C] token-major
+            q_tok = self._project(n_tok, (self.to_q.weight,), norm)                          # [T, C] token-major
             if hasattr(self.processor, "to_k_ip"):                                           # IP-Adapter dual-KV (config 4)
                 o = B200IPAttnProcessor.attend(self.processor, self, q_tok, ctx, n_frames, d, ctx_map)
                 return ops.linear(o, self.to_out[0].weight, f32(self.to_out[0].bias), residual=residual)
@@ -642,6 +712,10 @@ class _BasicTransformerBlock(nn.Module):
         return self.processor
 
     def native(self, h, n_frames, d, ctx, ctx_map):
+        if ln_foldable(h):
+            h = self.attn1.native(h, h, n_frames, d, norm=self.norm1)                       # attention.py:268-271
+            h = self.attn2.native(h, h, n_frames, d, ctx, ctx_map, norm=self.norm2)         # :273-286
+            return self.ff.native_ln(h, self.norm3)                                         # :289
         ln = lambda x, m: ops.layernorm_pe(x, f32(m.weight), f32(m.bias), m.eps)  # noqa: E731
         h = self.attn1.native(ln(h, self.norm1), h, n_frames, d)                            # attention.py:268-271
         h = self.attn2.native(ln(h, self.norm2), h, n_frames, d, ctx, ctx_map)              # :273-286

@@ -345,3 +345,58 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
                                    0 if r2 is None else r2.stride(0), y.stride(0), L.CA_EPI_GEGLU if geglu else L.CA_EPI_NONE,
                                    _dt(x), _stream()), "ca_linear")
     return y.reshape(*lead, n_out)
+
+
+def row_stats(x: torch.Tensor, eps: float = 1e-5, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(mean, rstd) of every row of the token matrix x [T, c] as fp32 pairs [T, 2] (ca_row_stats): the statistics half of a
+    LayerNorm whose normalisation is applied by `linear_ln`."""
+    _cuda(x)
+    if x.dim() != 2 or x.stride(1) != 1 or x.dtype not in (torch.bfloat16, torch.float16):
+        raise ValueError("row_stats: x must be a bf16/f16 token matrix with dense rows")
+    T, c = x.shape
+    st = torch.empty((T, 2), dtype=torch.float32, device=x.device) if out is None else out
+    with P.span("row_stats", 1, float(T * c * x.element_size() + 8 * T)):
+        L.check(L.load().ca_row_stats(x.data_ptr(), st.data_ptr(), T, c, x.stride(0), float(eps), _dt(x), _stream()), "ca_row_stats")
+    return st
+
+
+def fold_layernorm(w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                   pe: Optional[torch.Tensor] = None):
+    """Fold LayerNorm(gamma, beta) (+ a positional-encoding table pe [R, k]) into the projection w [n, k] (+ bias) behind it:
+    returns (w_gain [n, k] in w.dtype, colsum [n] fp32, shift [R or 1, n] fp32) for `linear_ln` — see ca_linear_ln."""
+    wf = w.detach().float()
+    w_gain = (wf * gamma.detach().float()[None, :]).to(w.dtype).contiguous()
+    colsum = w_gain.float().sum(dim=1).contiguous()
+    rows = beta.detach().float()[None, :]
+    if pe is not None:
+        rows = rows + pe.detach().float().reshape(-1, w.shape[1])
+    shift = rows @ wf.t()
+    if bias is not None:
+        shift = shift + bias.detach().float()[None, :]
+    return w_gain, colsum, shift.contiguous()
+
+
+def linear_ln(x: torch.Tensor, stats: torch.Tensor, w_gain: torch.Tensor, colsum: torch.Tensor, shift: torch.Tensor, *,
+              frames: int = 1, sites: int = 1, geglu: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Linear(LayerNorm(x) + pe[frame]) [-> a*gelu(g)] from the RAW rows x [T, k]: the tcgen05 GEMM runs on x with the
+    gain-folded weights and its epilogue applies the rows' (mean, rstd) and the per-frame shift (ca_linear_ln)."""
+    _cuda(x, stats, w_gain, colsum, shift)
+    if x.dim() != 2 or x.stride(1) != 1 or x.dtype != w_gain.dtype or x.dtype not in (torch.bfloat16, torch.float16):
+        raise ValueError("linear_ln: x must be a bf16/f16 token matrix of the weights' dtype")
+    m, k = x.shape
+    n = w_gain.shape[0]
+    if tuple(w_gain.shape) != (n, k) or not w_gain.is_contiguous():
+        raise ValueError("linear_ln: w_gain must be a contiguous [n, k] matrix")
+    if tuple(stats.shape) != (m, 2) or stats.dtype != torch.float32 or not stats.is_contiguous():
+        raise ValueError("linear_ln: stats must be row_stats(x)")
+    if colsum.dtype != torch.float32 or colsum.numel() != n or shift.dtype != torch.float32 or shift.dim() != 2 \
+            or shift.shape[1] != n or not shift.is_contiguous() or not colsum.is_contiguous():
+        raise ValueError("linear_ln: colsum [n] / shift [R, n] must be contiguous fp32 (fold_layernorm)")
+    n_out = n // 2 if geglu else n
+    y = torch.empty((m, n_out), dtype=x.dtype, device=x.device) if out is None else out.reshape(m, n_out)
+    nbytes = (m * k + n * k + m * n_out) * x.element_size() + 8 * m
+    with P.span("linear_tcgen05", 1, float(nbytes), 2.0 * m * n * k):
+        L.check(L.load().ca_linear_ln(x.data_ptr(), w_gain.data_ptr(), colsum.data_ptr(), shift.data_ptr(), shift.shape[0],
+                                      frames, sites, stats.data_ptr(), y.data_ptr(), m, n, k, x.stride(0), y.stride(0),
+                                      L.CA_EPI_GEGLU if geglu else L.CA_EPI_NONE, _dt(x), _stream()), "ca_linear_ln")
+    return y

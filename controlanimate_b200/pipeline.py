@@ -74,6 +74,12 @@ class MultiControlNetResiduals:
         self.cond_scale = [float(s) for s in cond_scale]
         self.prep_images: Optional[List[torch.Tensor]] = None
         self.lazy = True  # hand the UNet a ResidualSet (single-pass merge) instead of merged tensors
+        # overlap: every ControlNet runs on its own CUDA stream, forked off the caller's stream and joined by the first
+        # consumer of the ResidualSet (the skip adds after the UNet's down path, unet.py:567-576) — the nets do not depend
+        # on each other or on the UNet encoder, and their 16x16 / 8x8 levels leave most of the 148 SMs idle on their own
+        self.overlap = False
+        self._streams: List[torch.cuda.Stream] = []
+        self._pending = None
 
     def raw(self, control_model_input, t, controlnet_prompt_embeds, frame_count, nets=None, images=None, out=None,
             sample_offset: int = 0):
@@ -89,14 +95,46 @@ class MultiControlNetResiduals:
         ctx_map = (sample_offset + torch.arange(b * frame_count, device=x.device)) % n_prompts
         nets = list(range(len(self.controlnets))) if nets is None else list(nets)
         images = self.prep_images if images is None else images
-        return [self.controlnets[k](x, t, controlnet_prompt_embeds, images[k], ctx_map=ctx_map,
-                                    out=None if out is None else out[j]) for j, k in enumerate(nets)]
+        if not (self.overlap and self.lazy and x.is_cuda):
+            return [self.controlnets[k](x, t, controlnet_prompt_embeds, images[k], ctx_map=ctx_map,
+                                        out=None if out is None else out[j]) for j, k in enumerate(nets)]
+        from .layers import _ctx_i32
+        _ctx_i32(ctx_map)        # shared by every net: convert on the caller's stream, BEFORE the fork (the nets only hit the cache)
+        main = torch.cuda.current_stream(x.device)
+        while len(self._streams) < len(nets):
+            self._streams.append(torch.cuda.Stream(x.device))
+        fork = torch.cuda.Event()
+        fork.record(main)
+        per_net, events = [], []
+        for j, k in enumerate(nets):
+            side = self._streams[j]
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                per_net.append(self.controlnets[k](x, t, controlnet_prompt_embeds, images[k], ctx_map=ctx_map,
+                                                   out=None if out is None else out[j]))
+                ev = torch.cuda.Event()
+                ev.record(side)
+                events.append(ev)
+        self._pending = (events, (x, ctx_map, t, controlnet_prompt_embeds, images))
+        return per_net
+
+    def join(self, rset=None):
+        """Hand the outstanding side-stream work of the last raw() to `rset` (its first consumer waits), or wait now."""
+        pending, self._pending = self._pending, None
+        if pending is None:
+            return rset
+        if rset is not None:
+            return rset.produced_on(*pending)
+        cur = torch.cuda.current_stream()
+        for ev in pending[0]:
+            cur.wait_event(ev)
+        return None
 
     def __call__(self, control_model_input, t, controlnet_prompt_embeds, frame_count, image_embeds=None,
                  do_classifier_free_guidance=True, guess_mode=True):
         per_net = self.raw(control_model_input, t, controlnet_prompt_embeds, frame_count)
         if self.lazy:
-            rs = ResidualSet(per_net, self.cond_scale, frame_count, guess_mode)
+            rs = self.join(ResidualSet(per_net, self.cond_scale, frame_count, guess_mode))
             return rs, None
         return merge_controlnet_residuals(per_net, self.cond_scale, frame_count, guess_mode)     # :294-316
 
@@ -227,11 +265,13 @@ class DenoisingLoop:
             tr.wait_released(sp.unet_rank)
             mc.raw(model_in, t, prompt_embeds, f, nets=nets, images=images, out=[tr.out_views(j) for j in range(len(nets))],
                    sample_offset=offset)
+            mc.join()
             tr.publish(sp.unet_rank)
             return None
         down = None
         if mc is not None and sp.g == 1:                          # CFG split only: my row's ControlNets run here
-            down = ResidualSet(mc.raw(model_in, t, prompt_embeds, f, images=images, sample_offset=offset), mc.cond_scale, f, False)
+            down = mc.join(ResidualSet(mc.raw(model_in, t, prompt_embeds, f, images=images, sample_offset=offset),
+                                       mc.cond_scale, f, False))
         elif mc is not None:                                      # sharded: kernel (3) will read the owners' arenas over NVLink
             per_net, owners = [], []
             for k in range(sp.n_nets):
@@ -250,7 +290,7 @@ class DenoisingLoop:
         # the step, and the weights; the per-window control images are copied into graph-owned buffers before a replay
         key = (tuple(latents.shape), latents.dtype, tuple(prompt_embeds.shape), prompt_embeds.dtype, latents.device,
                float(self.guidance_scale), bool(self.guess_mode), tuple(mc.cond_scale) if mc is not None else (),
-               bool(mc.lazy) if mc is not None else None, tuple((tuple(im.shape), im.dtype) for im in images),
+               (bool(mc.lazy), bool(mc.overlap)) if mc is not None else None, tuple((tuple(im.shape), im.dtype) for im in images),
                self._weight_stamp())
         g = self._graphs.get(key)
         if g is None:

@@ -46,6 +46,21 @@ class ResidualSet:
         # native nets emit channels_last tensors; diffusers-style nets emit NCHW-contiguous ones
         t = self.per_net[0][1] if self.n_res > 1 else self.per_net[0][0]
         self.layout = L.CA_LAYOUT_BFHWC if t.is_contiguous(memory_format=torch.channels_last) else L.CA_LAYOUT_NCFHW
+        self._pending = None
+
+    def produced_on(self, events, keep=()) -> "ResidualSet":
+        """The per-net tensors are still being written on other streams (MultiControlNetResiduals.overlap): `events[k]` is
+        recorded behind net k's last kernel; the first consumer makes ITS stream wait for them.  `keep` holds the producers'
+        inputs alive until then (they were allocated on the consumer's stream)."""
+        self._pending = (list(events), keep)
+        return self
+
+    def _join(self) -> None:
+        if self._pending is not None:
+            cur = torch.cuda.current_stream()
+            for ev in self._pending[0]:
+                cur.wait_event(ev)
+            self._pending = None
 
     @staticmethod
     def coerce(down, mid, frames) -> Optional["ResidualSet"]:
@@ -59,6 +74,7 @@ class ResidualSet:
 
     def add_into(self, skips: Optional[Sequence[torch.Tensor]], mid: Optional[torch.Tensor]) -> None:
         """skips: 12 channels_last [(b f), c, h, w] tensors (in place); mid: the mid-block output (in place)."""
+        self._join()
         if self.layout == L.CA_LAYOUT_NCFHW:
             # diffusers-style NCHW residuals against native (BFHWC) skips: merge once into the reference layout
             # (one kernel, contract-preserving) and add that; the single-pass path needs native residuals.
@@ -76,6 +92,7 @@ class ResidualSet:
     def added_to(self, skip: torch.Tensor, index: int) -> torch.Tensor:
         """`skip + Σ_k s_k r_{k,index}` as a NEW tensor in the skip's layout: what the reference's UNet computes at
         unet.py:572 / :585 when it adds entry `index` of the residual tuple (the B3 drop-in route: see LazyResidual)."""
+        self._join()
         if skip.is_contiguous() or skip.permute(0, 2, 3, 4, 1).is_contiguous():
             out = skip.clone(memory_format=torch.preserve_format)
         else:                                   # a rearrange view of the reference: densify in the native layout
@@ -94,6 +111,7 @@ class ResidualSet:
         return tuple(LazyResidual(self, i) for i in range(n - 1)), LazyResidual(self, n - 1)
 
     def materialize(self) -> Tuple[Tuple[torch.Tensor, ...], torch.Tensor]:
+        self._join()
         return merge_controlnet_residuals(self.per_net, None, self.frames, scales=self.scales)
 
     def _materialize_lists(self):
@@ -148,6 +166,7 @@ class _MergedResiduals(ResidualSet):
 
     def __init__(self, down, mid, frames):
         self.down, self.mid, self.frames = down, mid, frames
+        self._pending = None
 
     def add_into(self, skips, mid):
         from .layers import video5

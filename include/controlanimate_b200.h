@@ -150,6 +150,20 @@ typedef enum { CA_EPI_NONE = 0, CA_EPI_GEGLU = 1 } ca_epilogue_t;
 int ca_linear(const void* x, const void* w, const float* bias, const void* residual, void* y, long long m, int n,
               int k, long long ldx, long long ldr, long long ldy, int epilogue, int dtype, void* stream);
 
+/* LayerNorm folded into the projection that consumes it.  With w_gain = w * diag(gamma) (rounded to dtype),
+ * colsum[n] = sum_k w_gain[n][k] and shift[r][n] = sum_k w[n][k] * (beta[k] + pe[r][k]) (+ bias[n]):
+ *   Linear(LayerNorm(x) + pe[frame])[row, n] = rstd[row] * (x[row] . w_gain[n] - mean[row] * colsum[n]) + shift[frame(row)][n]
+ * so the normalised tensor never exists in HBM: ca_row_stats reads x once and writes 8 bytes per row, ca_linear_ln runs the
+ * tcgen05 GEMM on the RAW rows and applies (mean, rstd) in its epilogue (also in front of GEGLU).
+ * Replaces nn.LayerNorm + PositionalEncoding + to_q/to_k/to_v (motion_module.py:214-215, 285-288, 321) and
+ * norm1/norm2/norm3 + the projections behind them (animatediff/models/attention.py:271-297).
+ *   stats [rows] (mean, rstd) fp32 pairs; shift [shift_rows, n] fp32 with shift_rows == 1 or >= frames, row
+ *   (token_row / sites) % frames is used (token rows are (b f d)-major; sites % 32 == 0 when shift_rows > 1) */
+int ca_row_stats(const void* x, float* stats, long long rows, int c, long long ldx, float eps, int dtype, void* stream);
+int ca_linear_ln(const void* x, const void* w_gain, const float* colsum, const float* shift, int shift_rows, int frames,
+                 int sites, const float* stats, void* y, long long m, int n, int k, long long ldx, long long ldy,
+                 int epilogue, int dtype, void* stream);
+
 /* Convolution epilogue on channels-last rows:  y = (act(x + bias) + residual) * scale.
  * Replaces the broadcast bias add behind every InflatedConv3d / nn.Conv2d of the path
  * (animatediff/models/resnet.py:12-20), the shortcut add and 1/output_scale_factor of

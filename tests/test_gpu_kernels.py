@@ -351,6 +351,66 @@ def test_linear_tcgen05(ops, m, n, k, dtype):
         assert relerr(y, a * torch.nn.functional.gelu(g)) <= REL[dtype]
 
 
+LN_FOLD_CASES = [
+    # T rows, k (LayerNorm width), n, frames, sites   (frames > 1: per-frame positional-encoding shift rows)
+    (4096, 320, 960, 16, 128), (2048, 320, 960, 5, 32), (1000, 320, 320, 1, 1), (6144, 640, 1920, 16, 64),
+    (2048, 1280, 3840, 16, 64), (3000, 64, 192, 1, 1), (20000, 320, 2560, 1, 1), (70000, 320, 960, 16, 4096),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("T,k,n,frames,sites", LN_FOLD_CASES)
+def test_layernorm_folded_into_projection(ops, T, k, n, frames, sites, dtype):
+    """ca_row_stats + ca_linear_ln == Linear(LayerNorm(x) + pe[frame]) (motion_module.py:214-215, 285-288 -> :321's to_q/k/v;
+    attention.py:271-297's norm1-3 -> projections), also in front of GEGLU, against the fp32 formula on the same bf16 rows.
+    Rows get a large common offset so that the epilogue's mean * colsum term really cancels something."""
+    T = T // (frames * sites) * frames * sites if frames > 1 else T
+    x = (synth.tensor(41, f"lnf.x.{T}.{k}", (T, k)) * 1.5 + synth.tensor(41, f"lnf.o.{T}", (T, 1)) * 4.0).to(dtype)
+    w = synth.tensor(41, f"lnf.w.{n}.{k}", (n, k), k ** -0.5).to(dtype)
+    gamma = 1.0 + synth.tensor(41, "lnf.g", (k,), 0.3)
+    beta = synth.tensor(41, "lnf.b", (k,), 0.2)
+    bias = synth.tensor(41, "lnf.bias", (n,), 0.1)
+    pe = synth.tensor(41, "lnf.pe", (24, k), 0.5) if frames > 1 else None
+    ln = torch.nn.functional.layer_norm(x.float(), (k,), gamma, beta, 1e-5)
+    if pe is not None:
+        frame_of = (torch.arange(T) // sites) % frames
+        ln = ln + pe[frame_of]
+    ref = torch.nn.functional.linear(ln, w.float(), bias)
+    xc = x.cuda()
+    st = ops.row_stats(xc, 1e-5)
+    mean, var = x.float().mean(1), x.float().var(1, unbiased=False)
+    assert torch.allclose(st[:, 0].cpu(), mean, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(st[:, 1].cpu(), torch.rsqrt(var + 1e-5), atol=0, rtol=1e-4)
+    w_gain, colsum, shift = ops.fold_layernorm(w.cuda(), gamma.cuda(), beta.cuda(), bias=bias.cuda(), pe=None if pe is None else pe.cuda())
+    assert shift.shape == (24 if pe is not None else 1, n)
+    y = ops.linear_ln(xc, st, w_gain, colsum, shift, frames=frames, sites=sites)
+    assert relerr(y, ref) <= 2 * REL[dtype]           # two roundings on the weights' side (w, then w * gamma)
+    if n % 64 == 0:
+        a, g = ref.chunk(2, dim=-1)
+        y = ops.linear_ln(xc, st, w_gain, colsum, shift, frames=frames, sites=sites, geglu=True)
+        assert y.shape == (T, n // 2)
+        assert relerr(y, a * torch.nn.functional.gelu(g)) <= 2 * REL[dtype]
+    # a strided view of a wider buffer (row stride > k) gives the same statistics
+    wide = torch.zeros((min(T, 512), k + 64), dtype=dtype, device="cuda")
+    wide[:, :k] = xc[:wide.shape[0]]
+    assert torch.equal(ops.row_stats(wide[:, :k], 1e-5), st[:wide.shape[0]])
+
+
+def test_layernorm_fold_contract_errors(ops):
+    x = torch.zeros((64, 64), dtype=torch.bfloat16, device="cuda")
+    st = ops.row_stats(x)
+    w_gain, colsum, shift = ops.fold_layernorm(torch.zeros((64, 64), dtype=torch.bfloat16, device="cuda"), torch.ones(64, device="cuda"),
+                                               torch.zeros(64, device="cuda"), pe=torch.zeros((8, 64), device="cuda"))
+    with pytest.raises((RuntimeError, ValueError)):
+        ops.linear_ln(x, st, w_gain, colsum, shift, frames=16, sites=32)      # 16 frames but an 8-row table
+    with pytest.raises((RuntimeError, ValueError)):
+        ops.linear_ln(x, st, w_gain, colsum, shift, frames=2, sites=24)       # sites not a multiple of 32
+    with pytest.raises(ValueError):
+        ops.linear_ln(x, st[:32], w_gain, colsum, shift)
+    with pytest.raises(ValueError):
+        ops.row_stats(x.float())
+
+
 def test_linear_strided_input_and_repeat(ops):
     """x may be a column slice of a wider buffer (row stride > k); repeated launches reuse barriers/TMEM cleanly."""
     buf = synth.tensor(32, "lin.buf", (512, 3 * 128)).bfloat16().cuda()
