@@ -315,13 +315,18 @@ def run_b200(args):
     sched = pipeline.DDIMScheduler()
     timesteps = sched.set_timesteps(n_steps)
     step_par = parallel.StepParallel(mode, rank, world, n_nets=n_nets) if mode in parallel.StepParallel.MODES else None
-    loop = pipeline.DenoisingLoop(unet, mc, sched, guidance_scale=guidance, use_cuda_graph=not args.no_graph, parallel=step_par,
-                                  use_lcm=lcm)
+    clip = None
+    if mode == "clip":
+        n_win = args.windows or (5 if world == 8 else max(1, world // 2))
+        clip = parallel.ClipLayout(rank, world, n_win, n_nets, args.local_nets or max(1, n_nets // 2))
+    else:
+        loop = pipeline.DenoisingLoop(unet, mc, sched, guidance_scale=guidance, use_cuda_graph=not args.no_graph, parallel=step_par,
+                                      use_lcm=lcm)
     windows = parallel.WindowParallel(rank, world, FRAMES, OVERLAP) if mode == "windows" else None
 
     f, lat = FRAMES, args.latent
     # windows: every rank has its own window of the clip; step parallelism: every rank works on THE SAME window
-    g = torch.Generator(device="cpu").manual_seed(100 + (rank if mode == "windows" else 0))
+    g = torch.Generator(device="cpu").manual_seed(100 + (rank if mode in ("windows", "clip") else 0))
     # host-side inputs (pinned): what a caller of the public API holds
     h_latents = torch.randn(1, 4, f, lat, lat, generator=g).pin_memory()
     rows = 1 if lcm else 2                                      # CFG duplicates the batch; the LCM branch does not
@@ -330,9 +335,20 @@ def run_b200(args):
     mc.prep_images = [im.to(dev) for im in h_images]          # prepared once per window (prep_control_images)
     d_prompt = h_prompt.to(dev)
     h_out = torch.empty_like(h_latents).pin_memory()
+    if clip is not None:
+        # the control video of job (window, net) lives on the rank that evaluates it
+        images = {}
+        for (w_, k_) in clip.jobs[rank]:
+            gi = torch.Generator(device="cpu").manual_seed(1000 + 10 * w_ + k_)
+            images[(w_, k_)] = torch.randn(rows * f, 3, lat * 8, lat * 8, generator=gi).to(dtype).to(dev)
+        mc.prep_images = None
+        loop = pipeline.ClipLoop(unet, mc, sched, clip, images, (1, 4, f, lat, lat), guidance_scale=guidance, use_lcm=lcm,
+                                 use_cuda_graph=not args.no_graph, overlap=OVERLAP)
 
     def one_step(latents, i):
         t = timesteps[i % n_steps]
+        if clip is not None:
+            return loop.step(latents if clip.is_unet_rank else None, t, d_prompt)
         latents = loop.step(latents, t, d_prompt)
         if windows is not None:
             latents = windows.exchange(latents)
@@ -373,6 +389,9 @@ def run_b200(args):
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for i in range(args.steps):
+        if clip is not None and not clip.is_unet_rank:       # a ControlNet server: its inputs arrive over NVLink
+            loop.step(None, timesteps[i % n_steps], d_prompt)
+            continue
         d_lat = h_latents.to(dev, non_blocking=True)
         d_p = h_prompt.to(dev, non_blocking=True)
         out = loop.step(d_lat, timesteps[i % n_steps], d_p)
@@ -419,7 +438,14 @@ def run_b200(args):
 
     if rank == 0:
         peaks = measured_peaks()
-        if mode == "windows" or world == 1:
+        if mode == "clip":
+            unique = clip.n_windows * f - (clip.n_windows - 1) * OVERLAP
+            counted = clip.n_windows * f
+            scaling = "strong"
+            par_desc = (f"clip layout: {clip.n_windows} UNet ranks (one {f}-frame window each, {clip.local_nets} ControlNet(s) local) + "
+                        f"{clip.n_servers} ControlNet server rank(s) for the other {sum(len(clip.jobs[r]) for r in range(clip.n_windows, world))} "
+                        f"(window, net) jobs; raw residuals read over NVLink by kernel (3); {unique} unique frames")
+        elif mode == "windows" or world == 1:
             unique = world * f - (world - 1) * OVERLAP          # adjacent windows share OVERLAP frames
             counted = world * f
             scaling = "weak"
@@ -498,7 +524,11 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames of the bounded CPU sample (>= 4: temporal attention is real)")
     ap.add_argument("--workload", default="config2", choices=["config2", "config3"],
                     help="config2 = the headline (BASELINE configs[1]); config3 = LCM + 4 ControlNets, 4 steps (configs[2])")
-    ap.add_argument("--parallelism", default="windows", choices=["windows", "cfg", "controlnet", "cfg+controlnet"],
+    ap.add_argument("--windows", type=int, default=0, help="clip layout: UNet ranks = windows of the clip (default: 5 of 8 ranks, "
+                    "else half the ranks); the other ranks serve ControlNet jobs")
+    ap.add_argument("--local-nets", type=int, default=0, help="clip layout: ControlNets a UNet rank evaluates itself "
+                    "(0 = half of them: measured best for config 3 on 8 GPUs, profiles/r02d_*)")
+    ap.add_argument("--parallelism", default="windows", choices=["windows", "cfg", "controlnet", "cfg+controlnet", "clip"],
                     help="how N > 1 GPUs are used (see the module docstring)")
     ap.add_argument("--no-eager-yardstick", dest="eager_yardstick", action="store_false",
                     help="skip the torch bf16 eager yardstick (the reference's op sequence under stock PyTorch on the same GPU)")

@@ -267,3 +267,90 @@ class SymmetricResiduals:
 
     def wait_released(self, from_rank: int):
         self.handle.wait_signal(from_rank, channel=1)
+
+
+class ClipLayout:
+    """Rank layout of a whole clip on one box (the 8-GPU plan of BASELINE config 3): `n_windows` UNet ranks —
+    rank w owns window w and evaluates the first `local_nets` ControlNets of its own window — and `world - n_windows`
+    SERVER ranks that evaluate the remaining (window, net) jobs, dealt window-major in contiguous, balanced runs (config 3 on
+    8 GPUs: 5 windows x 4 nets -> 5 local jobs + 15 served ones, 5 per server).  A UNet rank ships its latents to its
+    servers at the start of a step and reads their raw residuals over NVLink in kernel (3) (`ClipTransport`)."""
+
+    def __init__(self, rank: int, world: int, n_windows: int, n_nets: int, local_nets: int = 1):
+        if not (1 <= n_windows <= world):
+            raise ValueError(f"{n_windows} windows need at least as many ranks (got {world})")
+        if not (0 <= local_nets <= n_nets):
+            raise ValueError("local_nets must be within [0, n_nets]")
+        self.rank, self.world, self.n_windows, self.n_nets = rank, world, n_windows, n_nets
+        self.n_servers = world - n_windows
+        if self.n_servers == 0:
+            local_nets = n_nets                      # nobody to serve: every window evaluates all of its own nets
+        self.local_nets = local_nets
+        served = [(w, k) for w in range(n_windows) for k in range(local_nets, n_nets)]
+        if served and self.n_servers > len(served):
+            raise ValueError(f"{self.n_servers} server ranks for {len(served)} ControlNet jobs: a server would idle")
+        self.jobs = {r: [] for r in range(world)}                  # rank -> [(window, net)] in evaluation order
+        for w in range(n_windows):
+            self.jobs[w] = [(w, k) for k in range(local_nets)]
+        for s in range(self.n_servers):                            # contiguous balanced split of the served jobs
+            lo, hi = s * len(served) // self.n_servers, (s + 1) * len(served) // self.n_servers
+            self.jobs[n_windows + s] = served[lo:hi]
+        self._owner = {job: r for r, js in self.jobs.items() for job in js}
+
+    @property
+    def is_unet_rank(self) -> bool:
+        return self.rank < self.n_windows
+
+    @property
+    def window(self) -> Optional[int]:
+        return self.rank if self.is_unet_rank else None
+
+    def unet_ranks(self) -> List[int]:
+        return list(range(self.n_windows))
+
+    def owner_of(self, window: int, net: int) -> int:
+        return self._owner[(window, net)]
+
+    def slot_of(self, window: int, net: int) -> int:
+        """Arena slot of the job on its owner (position in the owner's job list)."""
+        return self.jobs[self.owner_of(window, net)].index((window, net))
+
+    def servers_of(self, window: int) -> List[int]:
+        return sorted({self.owner_of(window, k) for k in range(self.local_nets, self.n_nets)})
+
+    def windows_of(self, server: int) -> List[int]:
+        """Windows a server works for, in the order it serves them."""
+        out: List[int] = []
+        for w, _ in self.jobs[server]:
+            if w not in out:
+                out.append(w)
+        return out
+
+    def max_slots(self) -> int:
+        return max(len(js) for js in self.jobs.values())
+
+
+class ClipTransport(SymmetricResiduals):
+    """SymmetricResiduals (raw residual arenas + publish / release signals) plus the per-step latent hand-off of a
+    ClipLayout: a second symmetric buffer with one latent slot per window; UNet rank w stores its window's latents into slot
+    w of each of its servers (a peer write over NVLink) and raises a signal the server's stream waits on."""
+
+    def __init__(self, shapes, slots: int, dtype, device, n_windows: int, latent_shape: Sequence[int], latent_dtype, group=None):
+        super().__init__(shapes, slots, dtype, device, group)
+        import torch.distributed._symmetric_memory as symm_mem
+        self.latent_shape = tuple(int(v) for v in latent_shape)
+        self.latent_numel = 1
+        for v in self.latent_shape:
+            self.latent_numel *= v
+        self.latent_dtype, self.n_windows = latent_dtype, n_windows
+        self.lat = symm_mem.empty(n_windows * self.latent_numel, dtype=latent_dtype, device=device)
+        self.lat_handle = symm_mem.rendezvous(self.lat, group if group is not None else dist.group.WORLD)
+
+    def send_latents(self, server: int, window: int, latents: torch.Tensor):
+        peer = self.lat_handle.get_buffer(server, (self.n_windows, self.latent_numel), self.latent_dtype, 0)
+        peer[window].copy_(latents.reshape(-1))
+        self.lat_handle.put_signal(server, channel=0)
+
+    def recv_latents(self, window: int, from_rank: int) -> torch.Tensor:
+        self.lat_handle.wait_signal(from_rank, channel=0)
+        return self.lat.view(self.n_windows, self.latent_numel)[window].view(self.latent_shape)

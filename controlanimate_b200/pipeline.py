@@ -346,3 +346,127 @@ class DenoisingLoop:
         for t in self.scheduler.set_timesteps(num_inference_steps):
             latents = self.step(latents, t, prompt_embeds)
         return latents
+
+
+class ClipLoop:
+    """One denoising step of a WHOLE clip on one box (parallel.ClipLayout): UNet rank w advances window w, server ranks
+    evaluate ControlNet jobs for several windows; the raw residuals travel through symmetric memory and are scaled, summed
+    and added into the skips by kernel (3) reading the servers' arenas over NVLink (parallel.ClipTransport).
+
+    images[(w, k)]: prepared control video of net k for window w ([(b f), 3, H, W], CFG-duplicated when CFG is on) — needed
+    on the rank that evaluates job (w, k).  Every rank calls `step` once per timestep: UNet ranks pass and get back their
+    window's latents (after the scheduler step and the overlap blend with the neighbouring windows), server ranks pass None.
+    """
+
+    def __init__(self, unet: UNet3DConditionModel, controlnets: MultiControlNetResiduals, scheduler: DDIMScheduler, layout,
+                 images: dict, latent_shape: Sequence[int], guidance_scale: float = 7.5, use_lcm: bool = False,
+                 use_cuda_graph: bool = False, overlap: int = 4, unet_group=None, group=None):
+        from .parallel import ClipTransport, WindowParallel
+        self.unet, self.mc, self.scheduler, self.layout, self.images = unet, controlnets, scheduler, layout, images
+        self.base = DenoisingLoop(unet, controlnets, scheduler, guidance_scale=guidance_scale, use_lcm=use_lcm)
+        self.use_cuda_graph, self._graph = use_cuda_graph, None
+        b, _, f, hh, ww = latent_shape
+        self.frames = f
+        rows = (2 if self.base.do_cfg else 1) * f
+        cn = controlnets.controlnets[0]
+        boc, lpb = cn.config["block_out_channels"], cn.config["layers_per_block"]
+        shapes, h, w = [(rows, boc[0], hh, ww)], hh, ww
+        for i, c in enumerate(boc):
+            shapes += [(rows, c, h, w)] * lpb
+            if i != len(boc) - 1:
+                h, w = (h + 1) // 2, (w + 1) // 2
+                shapes.append((rows, c, h, w))
+        shapes.append((rows, boc[-1], h, w))
+        dtype, dev = unet.conv_in.weight.dtype, unet.conv_in.weight.device
+        self.transport = ClipTransport(shapes, layout.max_slots(), dtype, dev, layout.n_windows, latent_shape, torch.float32, group)
+        self.windows = WindowParallel(layout.rank, layout.n_windows, f, overlap, unet_group) if layout.is_unet_rank else None
+        if layout.is_unet_rank:      # the arenas start out free: the servers' first wait_released must not block
+            for s in layout.servers_of(layout.window):
+                self.transport.release(s)
+
+    # ---- UNet rank ---------------------------------------------------------------------------------------------------
+    def _unet_noise(self, latents: torch.Tensor, t, prompt_embeds: torch.Tensor) -> torch.Tensor:
+        lo, tr, mc, base = self.layout, self.transport, self.mc, self.base
+        w, f = lo.window, latents.shape[2]
+        for s in lo.servers_of(w):                                   # the servers start on this step's latents right away
+            tr.send_latents(s, w, latents.float())
+        cfg = base.do_cfg
+        model_in = torch.cat([latents] * 2) if cfg else latents
+        local = [k for _, k in lo.jobs[lo.rank]]
+        imgs = [self.images.get((w, k)) for k in range(lo.n_nets)]
+        mine = mc.raw(model_in, t, prompt_embeds, f, nets=local, images=imgs) if local else []
+        per_net, owners = [], []
+        for k in range(lo.n_nets):
+            if k in local:
+                per_net.append(mine[local.index(k)])
+            else:
+                per_net.append(tr.peer_views(lo.owner_of(w, k), lo.slot_of(w, k)))
+                owners.append(lo.owner_of(w, k))
+        down = mc.join(RemoteResidualSet(per_net, mc.cond_scale, f, False, tr, owners))
+        noise = self.unet(model_in, t, encoder_hidden_states=prompt_embeds, down_block_additional_residuals=down,
+                          timestep_cond=base._w_embedding(model_in)).sample.to(latents.dtype)
+        if cfg:
+            u, c = noise.chunk(2)
+            noise = u + base.guidance_scale * (c - u)
+        return noise
+
+    # ---- server rank -------------------------------------------------------------------------------------------------
+    def _serve(self, t, prompt_embeds) -> None:
+        lo, tr, mc = self.layout, self.transport, self.mc
+        cfg = self.base.do_cfg
+        for w in lo.windows_of(lo.rank):
+            latents = tr.recv_latents(w, w)                          # stream waits for UNet rank w's signal
+            tr.wait_released(w)                                      # ... and until it has consumed last step's residuals
+            model_in = torch.cat([latents] * 2) if cfg else latents
+            jobs = [(k, slot) for slot, (jw, k) in enumerate(lo.jobs[lo.rank]) if jw == w]
+            imgs = [self.images.get((w, k)) for k in range(lo.n_nets)]
+            prompt = prompt_embeds[w] if isinstance(prompt_embeds, (list, tuple, dict)) else prompt_embeds
+            mc.raw(model_in, t, prompt, self.frames, nets=[k for k, _ in jobs], images=imgs,
+                   out=[tr.out_views(slot) for _, slot in jobs])
+            mc.join()
+            tr.publish(w)
+
+    def _capture(self, fn, *static):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                                # warm-up (cuDNN algorithm selection, caches) — a full,
+            for _ in range(2):                                       # collective step on every rank, signals included
+                fn(*static)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = fn(*static)
+        return graph, out
+
+    @torch.no_grad()
+    def step(self, latents: Optional[torch.Tensor], t: int, prompt_embeds) -> Optional[torch.Tensor]:
+        lo = self.layout
+        if not self.use_cuda_graph:
+            if not lo.is_unet_rank:
+                self._serve(t, prompt_embeds)
+                return None
+            noise = self._unet_noise(latents, t, prompt_embeds)
+        else:
+            if self._graph is None:
+                dev = self.unet.conv_in.weight.device
+                s_t = torch.full((1,), int(t), dtype=torch.int64, device=dev)
+                if lo.is_unet_rank:
+                    s_lat, s_prompt = latents.clone(), prompt_embeds.clone()
+                    graph, out = self._capture(self._unet_noise, s_lat, s_t, s_prompt)
+                    self._graph = dict(graph=graph, lat=s_lat, t=s_t, prompt=s_prompt, out=out)
+                else:
+                    graph, _ = self._capture(self._serve, s_t, prompt_embeds)
+                    self._graph = dict(graph=graph, t=s_t)
+                # the warm-up / capture passes exchanged signals in lock step on every rank; nothing is left pending
+            g = self._graph
+            g["t"].fill_(int(t))
+            if lo.is_unet_rank:
+                g["lat"].copy_(latents, non_blocking=True)
+                if prompt_embeds.data_ptr() != g["prompt"].data_ptr():
+                    g["prompt"].copy_(prompt_embeds, non_blocking=True)
+            g["graph"].replay()
+            if not lo.is_unet_rank:
+                return None
+            noise = g["out"]
+        latents = self.scheduler.step(noise, int(t), latents)
+        return self.windows.exchange(latents)

@@ -42,6 +42,48 @@ def main():
             got = parallel.WindowParallel(rank, world, frames, ov).exchange(wins[rank].to(dev))
             torch.cuda.synchronize()
             assert torch.allclose(got, want, atol=1e-6), float((got - want).abs().max())
+        elif mode == "clip":
+            # parallel.ClipLayout: world // 2 windows (UNet ranks) + the rest ControlNet servers, 4 nets, LCM branch (b = 1)
+            # and CFG (b = 2); every UNet rank must end each step with what the windows computed alone and blended give
+            n_win, n_nets, f, hh, ov = max(1, world // 2), 4, 8, 16, 2
+            cfg = utils.sd15_unet3d_config(time_cond_proj_dim=256)
+            cfg.update(block_out_channels=(64, 128, 256, 256), cross_attention_dim=64)
+            dtype = torch.bfloat16
+            unet = utils.build_on_device(lambda: un.UNet3DConditionModel(**cfg), dev, dtype, seed=1)
+            nets = [utils.build_on_device(lambda: un.ControlNetModel(block_out_channels=cfg["block_out_channels"], cross_attention_dim=64),
+                                          dev, dtype, seed=2 + k) for k in range(n_nets)]
+            scales = [1.0, 0.35, 1.0, 0.4]
+            sched = pipeline.DDIMScheduler()
+            ts = sched.set_timesteps(4)
+            for lcm in (True, False):
+                rows = 1 if lcm else 2
+                g = torch.Generator().manual_seed(3)                    # identical inputs on every rank
+                lats = [torch.randn(1, 4, f, hh, hh, generator=g).to(dev) for _ in range(n_win)]
+                prompt = torch.randn(rows, 7, 64, generator=g).to(dev, dtype)
+                images = {(w, k): torch.randn(rows * f, 3, hh * 8, hh * 8, generator=g).to(dev, dtype)
+                          for w in range(n_win) for k in range(n_nets)}
+                want = [x.clone() for x in lats]
+                for t in ts[:3]:                                        # every window alone, then the overlap blend
+                    nxt = []
+                    for w in range(n_win):
+                        mc = pipeline.MultiControlNetResiduals(nets, scales)
+                        mc.prep_images = [images[(w, k)] for k in range(n_nets)]
+                        alone = pipeline.DenoisingLoop(unet, mc, sched, guidance_scale=7.5, use_lcm=lcm)
+                        nxt.append(alone.step(want[w], t, prompt))
+                    want = parallel.blend_windows_reference(nxt, ov)
+                for graph in (False, True):
+                    layout = parallel.ClipLayout(rank, world, n_win, n_nets, local_nets=1)
+                    mc = pipeline.MultiControlNetResiduals(nets, scales)
+                    loop = pipeline.ClipLoop(unet, mc, sched, layout, {j: images[j] for j in layout.jobs[rank]}, (1, 4, f, hh, hh),
+                                             guidance_scale=7.5, use_lcm=lcm, use_cuda_graph=graph, overlap=ov)
+                    cur = lats[rank].clone() if layout.is_unet_rank else None
+                    for t in ts[:3]:
+                        cur = loop.step(cur, t, prompt)
+                    torch.cuda.synchronize()
+                    if layout.is_unet_rank:
+                        c = cosine(cur, want[rank])
+                        assert c >= 0.9999, (mode, lcm, graph, rank, c)
+                    dist.barrier()
         else:
             cfg = utils.sd15_unet3d_config()
             cfg.update(block_out_channels=(64, 128, 256, 256), cross_attention_dim=64)

@@ -292,3 +292,18 @@ def test_motion_module_through_fused_temporal_block():
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", __file__, "-k",
                         "test_motion_module_b2 or test_unet3d_forward"], env=child_env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_model_with_layernorm_folded_into_the_projections():
+    """CA_LN_FOLD=1 (read once per process) runs every LayerNorm -> projection pair of the motion modules and the spatial
+    transformers as ca_row_stats + ca_linear_ln; the B2 / UNet / full-step parity cases are re-run in a child process."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("CA_FUSED_CHILD") == "1":
+        pytest.skip("already inside a child run")
+    child_env = dict(os.environ, CA_FUSED_CHILD="1", CA_LN_FOLD="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", __file__, "-k",
+                        "test_motion_module_b2 or test_unet3d_forward or test_denoising_step_with_controlnets"],
+                       env=child_env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

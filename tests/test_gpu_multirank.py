@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("mode,world", [("windows", 2), ("cfg", 2), ("controlnet", 2), ("controlnet", 3), ("cfg+controlnet", 4)])
+@pytest.mark.parametrize("mode,world", [("windows", 2), ("cfg", 2), ("controlnet", 2), ("controlnet", 3), ("cfg+controlnet", 4), ("clip", 3), ("clip", 4)])
 def test_multirank(mode, world):
     if not torch.cuda.is_available():
         pytest.fail("GPU tests need a CUDA device")

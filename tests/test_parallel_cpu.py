@@ -127,3 +127,27 @@ def _combine_worker(rank, world):
 @pytest.mark.parametrize("world", [2, 4])
 def test_step_parallel_combine_noise(world):
     _run(_combine_worker, world)
+
+
+def test_clip_layout_is_the_survey_plan_for_config_3():
+    """8 GPUs, 5 windows x 4 ControlNets -> ranks 0-4 = UNet_w + one ControlNet of window w, ranks 5-7 = the other
+    15 jobs, 5 each; every job has exactly one owner and a UNet rank's remote sets come from at most two servers."""
+    from controlanimate_b200.parallel import ClipLayout
+    lay = [ClipLayout(r, 8, 5, 4) for r in range(8)]
+    jobs = [j for r in range(8) for j in lay[0].jobs[r]]
+    assert sorted(jobs) == [(w, k) for w in range(5) for k in range(4)]
+    assert all(lay[0].jobs[w] == [(w, 0)] for w in range(5)) and all(len(lay[0].jobs[s]) == 5 for s in (5, 6, 7))
+    assert lay[0].max_slots() == 5 and [lay[w].is_unet_rank for w in range(8)] == [True] * 5 + [False] * 3
+    for w in range(5):
+        assert 1 <= len(lay[0].servers_of(w)) <= 2
+        for k in range(1, 4):
+            o = lay[0].owner_of(w, k)
+            assert lay[0].jobs[o][lay[0].slot_of(w, k)] == (w, k) and w in lay[0].windows_of(o)
+    # no server ranks: plain windows, every net local;  more local nets: fewer served jobs
+    assert ClipLayout(0, 4, 4, 4).jobs[2] == [(2, k) for k in range(4)] and ClipLayout(0, 4, 4, 4).servers_of(1) == []
+    two = ClipLayout(0, 8, 5, 4, local_nets=2)
+    assert sorted(len(two.jobs[s]) for s in (5, 6, 7)) == [3, 3, 4]
+    with pytest.raises(ValueError):
+        ClipLayout(0, 4, 5, 4)
+    with pytest.raises(ValueError):
+        ClipLayout(0, 8, 1, 4, local_nets=2)       # 7 servers for 2 served jobs
