@@ -130,6 +130,22 @@ def conv_bias(conv: nn.Conv2d, x4: torch.Tensor, *, silu: bool = False, residual
     return ops.bias_act_residual(y, bias, residual, silu=silu, inplace=True)
 
 
+def concat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """torch.cat([a, b], dim=1) of two [(b f), c, h, w] tensors; one streaming kernel when both are channels_last 16-bit."""
+    a, b = _cl(a), _cl(b)
+    if a.is_cuda and a.dtype == b.dtype and a.shape[1] % 8 == 0 and b.shape[1] % 8 == 0 and a.dtype != torch.float32:
+        return ops.concat_channels(a, b)
+    return torch.cat([a, b], dim=1)
+
+
+def upsample_nearest(x: torch.Tensor, size=None) -> torch.Tensor:
+    """F.interpolate(mode="nearest") by 2 or to `size` (Upsample3D.forward, resnet.py:63-69)."""
+    x = _cl(x)
+    if x.is_cuda and x.shape[1] % 8 == 0 and x.dtype != torch.float32:
+        return ops.upsample_nearest(x, size)
+    return F.interpolate(x, size=size, mode="nearest") if size is not None else F.interpolate(x, scale_factor=2.0, mode="nearest")
+
+
 def sum_f32(owner: nn.Module, *ps: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     """fp32 sum of small parameter vectors (folded biases), cached ON THE OWNING MODULE until one of them changes —
     the cache dies with the module, so a recycled id()/address of a later model can never hit a stale entry."""

@@ -400,3 +400,37 @@ def linear_ln(x: torch.Tensor, stats: torch.Tensor, w_gain: torch.Tensor, colsum
                                       frames, sites, stats.data_ptr(), y.data_ptr(), m, n, k, x.stride(0), y.stride(0),
                                       L.CA_EPI_GEGLU if geglu else L.CA_EPI_NONE, _dt(x), _stream()), "ca_linear_ln")
     return y
+
+
+def _is_cl(t: torch.Tensor) -> bool:
+    return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def upsample_nearest(x: torch.Tensor, size: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """F.interpolate(x, scale_factor=2.0 | size=size, mode="nearest") for a channels_last [n, c, h, w] tensor
+    (Upsample3D.forward, resnet.py:63-69) as one streaming copy (ca_upsample_nearest)."""
+    _cuda(x)
+    if not _is_cl(x):
+        raise ValueError("upsample_nearest: x must be a channels_last [n, c, h, w] tensor")
+    n, c, h, w = x.shape
+    oh, ow = (2 * h, 2 * w) if size is None else (int(size[0]), int(size[1]))
+    y = torch.empty((n, c, oh, ow), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    with P.span("copy_ops", 1, float((x.numel() + y.numel()) * x.element_size())):
+        L.check(L.load().ca_upsample_nearest(x.data_ptr(), y.data_ptr(), n, c, h, w, oh, ow, 1 if size is None else 0, _dt(x),
+                                             _stream()), "ca_upsample_nearest")
+    return y
+
+
+def concat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """torch.cat([a, b], dim=1) for channels_last [n, c, h, w] tensors (the skip concat of the up blocks,
+    unet_blocks.py:636, :742) as one streaming copy (ca_concat_channels)."""
+    _cuda(a, b)
+    if not (_is_cl(a) and _is_cl(b)) or a.dtype != b.dtype or a.shape[0] != b.shape[0] or a.shape[2:] != b.shape[2:]:
+        raise ValueError("concat_channels: a and b must be channels_last [n, c, h, w] tensors of one dtype and spatial size")
+    n, ca, h, w = a.shape
+    cb = b.shape[1]
+    y = torch.empty((n, ca + cb, h, w), dtype=a.dtype, device=a.device, memory_format=torch.channels_last)
+    with P.span("copy_ops", 1, float(2 * y.numel() * y.element_size())):
+        L.check(L.load().ca_concat_channels(a.data_ptr(), b.data_ptr(), y.data_ptr(), n * h * w, ca, cb, _dt(a), _stream()),
+                "ca_concat_channels")
+    return y

@@ -254,13 +254,10 @@ class UNet3DConditionModel(nn.Module):
             n = len(blk.resnets)
             rs, skips = skips[-n:], skips[:-n]
             for j in range(n):
-                x = torch.cat([x, rs.pop()], dim=1)
+                x = Ly.concat_channels(x, rs.pop())                                        # unet_blocks.py:636, :742
                 x = blk.layer(j, x, emb, frames, ctx, None, next(shifts))
             if hasattr(blk, "upsamplers"):
-                if forward_upsample_size:
-                    x = F.interpolate(x, size=tuple(skips[-1].shape[-2:]), mode="nearest")
-                else:
-                    x = F.interpolate(x, scale_factor=2.0, mode="nearest")                 # resnet.py:63-66
+                x = Ly.upsample_nearest(x, tuple(skips[-1].shape[-2:]) if forward_upsample_size else None)  # resnet.py:63-69
                 x = Ly.conv_bias(blk.upsamplers[0].conv, x)
 
         x = Ly.group_norm(x, self.conv_norm_out, frames, per_frame=self.per_frame, silu=True)  # :614-615

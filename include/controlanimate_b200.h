@@ -174,6 +174,17 @@ int ca_linear_ln(const void* x, const void* w_gain, const float* colsum, const f
 int ca_bias_act_residual(const void* x, const float* bias, const void* residual, void* y, long long rows, int c,
                          float scale, int act, int dtype, void* stream);
 
+/* The two pure data-movement steps of the UNet's up path, on channels-last rows ([n, h, w, c] memory order):
+ *   ca_upsample_nearest: F.interpolate(mode="nearest") of Upsample3D.forward (animatediff/models/resnet.py:63-69);
+ *     exact_2x = 1 -> scale_factor 2 (out = 2 * in), else to the explicit (out_h, out_w) of forward_upsample_size
+ *     (unet.py:491-499, 596-597) with torch's source index min(floor(dst * in / out), in - 1)
+ *   ca_concat_channels: torch.cat([hidden_states, res_hidden_states], dim=1) in front of every up-block resnet
+ *     (animatediff/models/unet_blocks.py:636, :742): y[r] = [a[r], b[r]] for rows = n * h * w
+ *   c, ca, cb multiples of 16 / sizeof(dtype); 16-byte aligned pointers; x / a / b / y dense */
+int ca_upsample_nearest(const void* x, void* y, long long n, int c, int in_h, int in_w, int out_h, int out_w, int exact_2x,
+                        int dtype, void* stream);
+int ca_concat_channels(const void* a, const void* b, void* y, long long rows, int ca, int cb, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

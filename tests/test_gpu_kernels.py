@@ -467,3 +467,31 @@ def test_temporal_attention_fused_rejects_unbuilt_width(ops):
     v = torch.zeros(640, device="cuda")
     with pytest.raises(ValueError):
         ops.temporal_attention_fused(x, v, v, None, ops.pack_qkv_per_head(w, w, w, 8), w, v, batch=1, frames=16, sites=4, heads=8)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("n,c,h,w,size", [(4, 64, 8, 8, None), (3, 320, 7, 12, None), (2, 1280, 7, 4, (14, 7)), (2, 640, 14, 7, (27, 14)),
+                                          (1, 8, 5, 3, (9, 7)), (32, 640, 32, 32, None)])
+def test_upsample_nearest_is_torch_interpolate(ops, n, c, h, w, size, dtype):
+    """Upsample3D.forward's F.interpolate(mode="nearest") (resnet.py:63-69), by 2 and to the explicit sizes of an odd pyramid
+    (forward_upsample_size: config 4's 54 -> 27 -> 14 -> 7): a copy, so bit-exact against torch."""
+    x = synth.tensor(51, f"up.{n}.{c}.{h}.{w}", (n, c, h, w)).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    y = ops.upsample_nearest(x, size)
+    ref = (torch.nn.functional.interpolate(x, size=size, mode="nearest") if size is not None
+           else torch.nn.functional.interpolate(x, scale_factor=2.0, mode="nearest"))
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(y, ref)
+    with pytest.raises(ValueError):
+        ops.upsample_nearest(x.contiguous(), size)          # NCHW-contiguous: not the native layout
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("n,ca,cb,h,w", [(4, 64, 64, 8, 8), (3, 320, 640, 7, 12), (2, 1280, 1280, 7, 4), (1, 8, 24, 5, 3), (32, 320, 320, 64, 64)])
+def test_concat_channels_is_torch_cat(ops, n, ca, cb, h, w, dtype):
+    """The skip concat in front of every up-block resnet (unet_blocks.py:636, :742): bit-exact against torch.cat."""
+    a = synth.tensor(52, f"cat.a.{n}.{ca}.{h}", (n, ca, h, w)).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    b = synth.tensor(52, f"cat.b.{n}.{cb}.{h}", (n, cb, h, w)).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    y = ops.concat_channels(a, b)
+    assert y.is_contiguous(memory_format=torch.channels_last) and torch.equal(y, torch.cat([a, b], dim=1))
+    with pytest.raises(ValueError):
+        ops.concat_channels(a, b[:, :, :-1])
