@@ -328,6 +328,9 @@ LINEAR_CASES = [
     # round 2 tilings: contiguous tile ranges that straddle n-blocks with a resident B block
     # (bn = 240); 512-column single-stage tiles (two UMMA sub-tiles per A stage) for long K with narrow N
     (3000, 96, 64), (1500, 160, 320), (40000, 1920, 640), (33000, 640, 2560), (70000, 320, 1280), (20000, 1280, 1280),
+    # A-stationary schedule (K <= 320, at least one m-block of 256 rows per CTA pair, several n-blocks): the A tile of an
+    # m-block stays in shared memory while the pair walks its n-blocks; ragged last m-block, 1..5 resident k-blocks
+    (40000, 960, 320), (25000, 2560, 320), (19001, 640, 256), (30000, 192, 64), (21000, 384, 136), (50000, 320, 192),
 ]
 
 
