@@ -31,6 +31,7 @@ SIGNATURES = {
     "ca_cross_attn_core": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _vp, _f, _i, _vp]),
     "ca_bias_act_residual": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _f, _i, _i, _vp]),
     "ca_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _ll, _ll, _i, _i, _vp]),
+    "ca_spatial_attn_core": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _vp]),
     "ca_upsample_nearest": (_i, [_vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ca_concat_channels": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
     "ca_row_stats": (_i, [_vp, _vp, _ll, _i, _ll, _f, _i, _vp]),

@@ -233,6 +233,8 @@ def ln_foldable(h: torch.Tensor, sites: int = 32) -> bool:
 import os as _os
 
 _LN_FOLD = _os.environ.get("CA_LN_FOLD", "0") == "1"
+# CA_OWN_FMHA: the h*w x h*w self-attention core of the spatial transformers on ca_spatial_attn_core instead of torch SDPA
+_OWN_FMHA = _os.environ.get("CA_OWN_FMHA", "0") == "1"
 
 # CA_FUSED_TEMPORAL=1 routes the temporal-attention blocks of the 320-wide level through the one-launch kernel
 # (ca_temporal_attn_fused).  It is parity-green but, as measured in profiles/r02_fused_notes.md, still slower than the
@@ -685,6 +687,12 @@ class _SpatialAttention(nn.Module):
         hd = c // self.heads
         if not self.is_cross:
             qkv = self._project(n_tok, (self.to_q.weight, self.to_k.weight, self.to_v.weight), norm)
+            if _OWN_FMHA and hd % 8 == 0 and hd <= 64:
+                # own tcgen05 flash attention over the h*w sites (ca_spatial_attn_core), q / k / v read in place from the
+                # packed projection output
+                o = ops.spatial_attention_core(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], frames=n_frames, sites=d,
+                                               heads=self.heads, scale=self.scale)
+                return ops.linear(o, self.to_out[0].weight, f32(self.to_out[0].bias), residual=residual)
             qkv = qkv.reshape(n_frames, d, 3, self.heads, hd)
             q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))
         else:

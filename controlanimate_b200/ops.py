@@ -434,3 +434,25 @@ def concat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         L.check(L.load().ca_concat_channels(a.data_ptr(), b.data_ptr(), y.data_ptr(), n * h * w, ca, cb, _dt(a), _stream()),
                 "ca_concat_channels")
     return y
+
+
+def spatial_attention_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, frames: int, sites: int, heads: int,
+                           scale: Optional[float] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(q k^T scale) v over the sites of each frame, per head (ca_spatial_attn_core).  q / k / v: [frames * sites, C]
+    row matrices (dense rows, any row stride: e.g. column slices of the packed [T, 3C] projection output)."""
+    _cuda(q, k, v)
+    T, c = q.shape
+    if T != frames * sites or k.shape != q.shape or v.shape != q.shape or c % heads:
+        raise ValueError("spatial_attention_core: q, k, v must be [frames * sites, heads * head_dim]")
+    if q.dtype not in (torch.bfloat16, torch.float16) or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise ValueError("spatial_attention_core: bf16 or f16 only")
+    if q.stride(1) != 1 or k.stride(1) != 1 or v.stride(1) != 1:
+        raise ValueError("spatial_attention_core: rows must be dense")
+    hd = c // heads
+    o = torch.empty((T, c), dtype=q.dtype, device=q.device) if out is None else out
+    scale = hd ** -0.5 if scale is None else scale
+    with P.span("spatial_attn_core", 1, 4.0 * T * c * q.element_size(), 4.0 * frames * heads * float(sites) * sites * hd):
+        L.check(L.load().ca_spatial_attn_core(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), frames, sites, heads, hd,
+                                              q.stride(0), k.stride(0), v.stride(0), o.stride(0), float(scale), _dt(q), _stream()),
+                "ca_spatial_attn_core")
+    return o

@@ -174,6 +174,15 @@ int ca_linear_ln(const void* x, const void* w_gain, const float* colsum, const f
 int ca_bias_act_residual(const void* x, const float* bias, const void* residual, void* y, long long rows, int c,
                          float scale, int act, int dtype, void* stream);
 
+/* Spatial self-attention core: o = softmax(q k^T * scale) v over the `sites` (h*w) tokens of one frame, per head — the
+ * arithmetic of BasicTransformerBlock.attn1 (animatediff/models/attention.py:268-271) behind the reference's AttentionProcessor
+ * (modules/attention_processor.py:56-62 / :247-256).  tcgen05 / TMEM flash attention: scores and the output accumulator live in
+ * TMEM, one thread per query row computes the exponentials, P V consumes V as it lies in HBM (MN-major operand).
+ *   q, k, v: rows (frame * sites + site) with row strides ldq / ldk / ldv (elements), head h at columns [h * head_dim, ...)
+ *   — e.g. the three column blocks of the packed [T, 3C] projection output; o likewise with ldo.  head_dim % 8 == 0, <= 64. */
+int ca_spatial_attn_core(const void* q, const void* k, const void* v, void* o, int frames, int sites, int heads, int head_dim,
+                         long long ldq, long long ldk, long long ldv, long long ldo, float scale, int dtype, void* stream);
+
 /* The two pure data-movement steps of the UNet's up path, on channels-last rows ([n, h, w, c] memory order):
  *   ca_upsample_nearest: F.interpolate(mode="nearest") of Upsample3D.forward (animatediff/models/resnet.py:63-69);
  *     exact_2x = 1 -> scale_factor 2 (out = 2 * in), else to the explicit (out_h, out_w) of forward_upsample_size

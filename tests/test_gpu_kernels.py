@@ -498,3 +498,27 @@ def test_concat_channels_is_torch_cat(ops, n, ca, cb, h, w, dtype):
     assert y.is_contiguous(memory_format=torch.channels_last) and torch.equal(y, torch.cat([a, b], dim=1))
     with pytest.raises(ValueError):
         ops.concat_channels(a, b[:, :, :-1])
+
+
+SPATIAL_ATTN_CASES = [
+    # frames, sites, heads, head_dim, input scale
+    (2, 256, 2, 40, 1.0), (1, 300, 3, 40, 1.0), (2, 128, 1, 64, 1.0), (1, 1000, 2, 32, 2.5), (1, 77, 2, 40, 1.0),
+    (2, 1024, 8, 40, 1.5), (1, 648, 4, 40, 3.0), (1, 4096, 2, 40, 1.0),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("frames,sites,heads,hd,mag", SPATIAL_ATTN_CASES)
+def test_spatial_attention_core(ops, frames, sites, heads, hd, mag, dtype):
+    """ca_spatial_attn_core == softmax(q k^T / sqrt(hd)) v per (frame, head) over the sites (attention.py:268-271 through the
+    processor's attention arithmetic, attention_processor.py:56-62), q / k / v read as column slices of one packed [T, 3C]
+    buffer; ragged site counts (query and key tails), score ranges wide enough that the lazily raised maximum is exercised."""
+    c = heads * hd
+    T = frames * sites
+    qkv = (synth.tensor(61, f"sa.{frames}.{sites}.{heads}.{hd}", (T, 3 * c)) * mag).to(dtype)
+    q, k, v = (qkv[:, i * c:(i + 1) * c].float().reshape(frames, sites, heads, hd).transpose(1, 2) for i in range(3))
+    att = torch.softmax(q @ k.transpose(-1, -2) * hd ** -0.5, dim=-1)
+    ref = (att @ v).transpose(1, 2).reshape(T, c)
+    g = qkv.cuda()
+    o = ops.spatial_attention_core(g[:, :c], g[:, c:2 * c], g[:, 2 * c:], frames=frames, sites=sites, heads=heads)
+    assert relerr(o, ref) <= 2 * REL[dtype]          # P is rounded to the storage type before P V, like every flash kernel

@@ -307,3 +307,18 @@ def test_model_with_layernorm_folded_into_the_projections():
                         "test_motion_module_b2 or test_unet3d_forward or test_denoising_step_with_controlnets"],
                        env=child_env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_model_with_own_spatial_attention_core():
+    """CA_OWN_FMHA=1 (read once per process) routes the h*w x h*w self-attention of every spatial transformer whose head_dim
+    fits (<= 64) through ca_spatial_attn_core instead of torch SDPA; the UNet / full-step parity cases are re-run in a child."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("CA_FUSED_CHILD") == "1":
+        pytest.skip("already inside a child run")
+    child_env = dict(os.environ, CA_FUSED_CHILD="1", CA_OWN_FMHA="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", __file__, "-k",
+                        "test_unet3d_forward or test_denoising_step_with_controlnets"],
+                       env=child_env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
