@@ -447,16 +447,21 @@ class ClipLoop:
                 return None
             noise = self._unet_noise(latents, t, prompt_embeds)
         else:
+            key = (None if latents is None else (tuple(latents.shape), latents.dtype),
+                   tuple(prompt_embeds.shape) if torch.is_tensor(prompt_embeds) else None)
+            if self._graph is not None and self._graph["key"] != key:
+                raise ValueError("ClipLoop: the captured step was recorded for other input shapes; build a new loop (the capture "
+                                 "is collective: every rank would have to re-record at the same step)")
             if self._graph is None:
                 dev = self.unet.conv_in.weight.device
                 s_t = torch.full((1,), int(t), dtype=torch.int64, device=dev)
                 if lo.is_unet_rank:
                     s_lat, s_prompt = latents.clone(), prompt_embeds.clone()
                     graph, out = self._capture(self._unet_noise, s_lat, s_t, s_prompt)
-                    self._graph = dict(graph=graph, lat=s_lat, t=s_t, prompt=s_prompt, out=out)
+                    self._graph = dict(graph=graph, lat=s_lat, t=s_t, prompt=s_prompt, out=out, key=key)
                 else:
                     graph, _ = self._capture(self._serve, s_t, prompt_embeds)
-                    self._graph = dict(graph=graph, t=s_t)
+                    self._graph = dict(graph=graph, t=s_t, key=key)
                 # the warm-up / capture passes exchanged signals in lock step on every rank; nothing is left pending
             g = self._graph
             g["t"].fill_(int(t))
