@@ -687,7 +687,7 @@ class _SpatialAttention(nn.Module):
         hd = c // self.heads
         if not self.is_cross:
             qkv = self._project(n_tok, (self.to_q.weight, self.to_k.weight, self.to_v.weight), norm)
-            if _OWN_FMHA and hd % 8 == 0 and hd <= 64:
+            if _OWN_FMHA and hd % 8 == 0 and 16 <= hd <= 64:
                 # own tcgen05 flash attention over the h*w sites (ca_spatial_attn_core), q / k / v read in place from the
                 # packed projection output
                 o = ops.spatial_attention_core(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], frames=n_frames, sites=d,
