@@ -356,7 +356,83 @@ __global__ void __launch_bounds__(kThreads, 1)
       };
       // P is double buffered: this tile's buffer was last read by the P V of tile j - 2
       if (j >= 2) twait(&pv_done[t][j & 1], (uint32_t)(((j >> 1) - 1) & 1), timing, tw1);
-      for (;;) {
+      // ---- fast path: a full tile with a known reference.  Straight-line and software pipelined by one chunk: the block that
+      // issues the 32 exponentials of chunk k also holds the row sums, conversions and stores of chunk k - 1 and the maximum
+      // search of chunk k, so the MUFU pipe is fed while the other pipes work (with two softmax warps per scheduler nothing
+      // else hides those latencies).
+      bool done = false, tripped = false;
+      if (valid >= kTile && __all_sync(0xffffffffu, m_ref > -INFINITY)) {
+        tripped = true;   // (only read when the fast path falls through)
+        float pa[32], pb[32];
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+        const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_ref, -m_ref);
+        auto E = [&](const uint32_t (&sv)[32], float (&pv)[32]) {   // exponentials of one chunk
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), c2, nm2);
+            pv[i] = ex2f(x.x);
+            pv[i + 1] = ex2f(x.y);
+          }
+        };
+        auto F = [&](const float (&pv)[32], int cb) {               // row sums, conversion, stores of one chunk
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            acc0 = __fadd2_rn(acc0, make_float2(pv[i], pv[i + 1]));
+            acc1 = __fadd2_rn(acc1, make_float2(pv[i + 2], pv[i + 3]));
+          }
+          unsigned char* dst = p_row + (cb >> 1) * kChunkBytes;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 w;
+            w.x = pack_pair<T>(pv[8 * u + 0], pv[8 * u + 1]);
+            w.y = pack_pair<T>(pv[8 * u + 2], pv[8 * u + 3]);
+            w.z = pack_pair<T>(pv[8 * u + 4], pv[8 * u + 5]);
+            w.w = pack_pair<T>(pv[8 * u + 6], pv[8 * u + 7]);
+            const int unit = (cb & 1) * 4 + u;
+            *reinterpret_cast<uint4*>(dst + ((unit ^ sw) * 16)) = w;
+          }
+        };
+        tmem_ld32(s_addr, sa);
+        tmem_ld_wait();
+        tmem_ld32(s_addr + 32u, sb);
+        E(sa, pa);
+        tmem_ld_wait();
+        tmem_ld32(s_addr + 64u, sa);
+        E(sb, pb);
+        F(pa, 0);
+        tmem_ld_wait();
+        tmem_ld32(s_addr + 96u, sb);
+        E(sa, pa);
+        F(pb, 1);
+        tmem_ld_wait();
+        // Does the reference still hold?  No maximum search in this path: a score above m_ref + 8 shows as an exponential
+        // above 2^8, hence as a row sum above 2^8 (every term is >= 0; an overflow to inf trips it as well).  The test is
+        // conservative — a sum of many small terms can trip it too; the general path then sets the reference to the exact
+        // maximum, after which the sum of a 128-key tile cannot exceed 128.  The last chunk is tested on its raw scores so
+        // that S can be released before its exponentials are taken.
+        float m3 = -INFINITY, m3b = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          m3 = max2(m3, __uint_as_float(sb[i]));
+          m3b = max2(m3b, __uint_as_float(sb[i + 1]));
+        }
+        F(pa, 2);
+        const float part = (acc0.x + acc0.y) + (acc1.x + acc1.y);
+        const bool trip = !(part <= 256.0f) || max2(m3, m3b) * c > m_ref + kRaise;
+        if (!__any_sync(0xffffffffu, trip)) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[t]);     // S is in registers for good: the next tile's scores may overwrite it
+          E(sb, pb);
+          F(pb, 3);
+          sum0 = acc0.x + acc0.y;
+          sum1 = acc1.x + acc1.y;
+          sum2 = sum3 = 0.f;
+          done = true;
+        }
+        // else: fall through to the general path below, which raises the reference and repeats the tile (S is still intact)
+      }
+      for (; !done;) {
         const bool have_ref = __any_sync(0xffffffffu, m_ref > -INFINITY);   // false only before a row's first tile (warp-uniform)
         sum0 = sum1 = sum2 = sum3 = 0.f;
         nm = -m_ref;
@@ -377,7 +453,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         tmem_ld_wait();
         max_chunk(sb, 3);
         mx *= c;
-        const bool raise = mx > m_ref + kRaise;
+        // after a trip of the fast path's sum test the reference moves to the exact maximum whenever that is higher at all, so
+        // that the following tiles' sums stay below the trip level
+        const bool raise = mx > m_ref + kRaise || (tripped && mx > m_ref);
         if (!__any_sync(0xffffffffu, raise)) {
           // the common case: S has been read for good (its last chunk is in registers) — the tensor pipe may overwrite it
           // with the next tile's scores while the last quarter of the exponentials is still being computed
