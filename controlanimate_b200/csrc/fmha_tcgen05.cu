@@ -30,6 +30,10 @@ constexpr int kSoftmaxWarps = 8;           // two warp groups: warps 0-3 -> quer
 constexpr int kProducerWarp = kSoftmaxWarps, kMmaWarp = kSoftmaxWarps + 1, kAllocWarp = kSoftmaxWarps + 3;
 constexpr int kThreads = (kSoftmaxWarps + 4) * 32;
 constexpr int kChunkBytes = kTile * 128;   // one 64-column (128-byte) SWIZZLE_128B chunk of a 128-row tile: 16 KB
+#ifndef CA_FMHA_POLY_EVERY
+#define CA_FMHA_POLY_EVERY 3
+#endif
+constexpr int kPolyEvery = CA_FMHA_POLY_EVERY;   // every n-th pair of exponentials of the fast path on the FMA pipes (0: none)
 constexpr float kRaise = 8.0f;             // raise the running maximum only past this margin (log2 units)
 
 struct FmhaParams {
@@ -106,6 +110,23 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for a pair of x <= 8 on the FMA / ALU pipes instead of the MUFU: x = n + f with n = round(x), f in [-0.5, 0.5];
+// 2^f by a cubic (max relative error 7.5e-5, far below the rounding of P to 16 bits) and n added into the exponent field.
+// The softmax pass is bound by the 16 exponentials per clock the MUFU pipe delivers; a third of them go this way
+// (measured, 4096^2 x 40: none 1683 us, every 4th pair 1600, every 3rd 1568, every 2nd 1794).
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);   // 1.5 * 2^23: the sum's low mantissa bits are round(x)
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 f = __fadd2_rn(x, __fadd2_rn(magic, make_float2(-t.x, -t.y)));   // x - (t - magic)
+  float2 q = __ffma2_rn(make_float2(5.517202416e-02f, 5.517202416e-02f), f, make_float2(2.426111656e-01f, 2.426111656e-01f));
+  q = __ffma2_rn(q, f, make_float2(6.932609214e-01f, 6.932609214e-01f));
+  q = __ffma2_rn(q, f, make_float2(9.999280683e-01f, 9.999280683e-01f));
+  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
+}
+
 template <typename T>
 __device__ __forceinline__ uint32_t pack_pair(float lo, float hi);
 template <>
@@ -366,12 +387,18 @@ __global__ void __launch_bounds__(kThreads, 1)
         float pa[32], pb[32];
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
         const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_ref, -m_ref);
-        auto E = [&](const uint32_t (&sv)[32], float (&pv)[32]) {   // exponentials of one chunk
+        auto E = [&](const uint32_t (&sv)[32], float (&pv)[32]) {   // exponentials of one chunk: 3 of 4 pairs on the MUFU
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), c2, nm2);
-            pv[i] = ex2f(x.x);
-            pv[i + 1] = ex2f(x.y);
+            if (kPolyEvery > 0 && (i / 2) % (kPolyEvery > 0 ? kPolyEvery : 1) == 0) {
+              const float2 e = ex2_poly2(x);
+              pv[i] = e.x;
+              pv[i + 1] = e.y;
+            } else {
+              pv[i] = ex2f(x.x);
+              pv[i + 1] = ex2f(x.y);
+            }
           }
         };
         auto F = [&](const float (&pv)[32], int cb) {               // row sums, conversion, stores of one chunk
