@@ -165,3 +165,26 @@ def test_ctx_map_is_converted_once():
     a = layers._ctx_i32(m)
     assert a.dtype == torch.int32 and a.tolist() == [0, 1, 2, 0, 1, 2]
     assert layers._ctx_i32(m) is a
+
+
+def test_fold_layernorm_algebra():
+    """ops.fold_layernorm (host side of ca_linear_ln): with w_gain = w * gamma, colsum = sum_k w_gain and shift = (beta + pe) w^T
+    + bias, rstd * (x w_gain^T - mean * colsum) + shift[frame] equals Linear(LayerNorm(x) + pe[frame]) (motion_module.py:214-215,
+    285-288 -> :321) — checked in fp32 on the CPU, where no kernel is involved."""
+    import torch
+    from controlanimate_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    T, k, n, frames, sites = 96, 64, 48, 4, 8
+    x = torch.randn(T, k, generator=g) * 2 + 3
+    w, bias = torch.randn(n, k, generator=g) * k ** -0.5, torch.randn(n, generator=g)
+    gamma, beta, pe = torch.rand(k, generator=g) + 0.5, torch.randn(k, generator=g), torch.randn(frames + 2, k, generator=g)
+    w_gain, colsum, shift = ops.fold_layernorm(w, gamma, beta, bias=bias, pe=pe)
+    assert w_gain.shape == (n, k) and colsum.shape == (n,) and shift.shape == (frames + 2, n)
+    mean, var = x.mean(1, keepdim=True), x.var(1, unbiased=False, keepdim=True)
+    rstd = torch.rsqrt(var + 1e-5)
+    frame_of = (torch.arange(T) // sites) % frames
+    got = rstd * (x @ w_gain.t() - mean * colsum[None, :]) + shift[frame_of]
+    want = torch.nn.functional.linear(torch.nn.functional.layer_norm(x, (k,), gamma, beta, 1e-5) + pe[frame_of], w, bias)
+    assert torch.allclose(got, want, atol=2e-4, rtol=1e-4)
+    # without a positional-encoding table the shift has one row
+    assert ops.fold_layernorm(w, gamma, beta)[2].shape == (1, n)
