@@ -504,6 +504,7 @@ SPATIAL_ATTN_CASES = [
     # frames, sites, heads, head_dim, input scale
     (2, 256, 2, 40, 1.0), (1, 300, 3, 40, 1.0), (2, 128, 1, 64, 1.0), (1, 1000, 2, 32, 2.5), (1, 77, 2, 40, 1.0),
     (2, 1024, 8, 40, 1.5), (1, 648, 4, 40, 3.0), (1, 4096, 2, 40, 1.0),
+    (1, 5184, 1, 40, 1.0), (1, 1296, 2, 40, 2.0), (3, 130, 2, 16, 1.0),      # config 4's 96 x 54 latents (and their 48 x 27 level)
 ]
 
 
