@@ -301,10 +301,11 @@ def run_b200(args):
     torch.backends.cudnn.benchmark = True
 
     mode = args.parallelism if world > 1 else "single"
-    lcm = args.workload == "config3"
-    n_steps = CONFIG3["steps"] if lcm else DDIM_STEPS
-    cond_scale = CONFIG3["cond_scale"] if lcm else COND_SCALE
-    guidance = CONFIG3["guidance"] if lcm else GUIDANCE
+    c3 = args.workload in ("config3", "config3-cfg")           # config 3: 4 ControlNets, 4 steps
+    lcm = args.workload == "config3"                           # ... in the LCM branch (b = 1); "config3-cfg": CFG 1.1, b = 2
+    n_steps = CONFIG3["steps"] if c3 else DDIM_STEPS
+    cond_scale = CONFIG3["cond_scale"] if c3 else COND_SCALE
+    guidance = CONFIG3["guidance"] if c3 else GUIDANCE
     n_nets = len(cond_scale)
     cfg = utils.sd15_unet3d_config(time_cond_proj_dim=256 if lcm else None)
     dtype = torch.bfloat16
@@ -464,9 +465,10 @@ def run_b200(args):
             "metric": "denoised frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(args, parallelism=par_desc) if not lcm else {
-                "workload": f"config 3: SD1.5 UNet3D (time_cond_proj_dim 256) + motion modules + 4 ControlNets {cond_scale}, LCM branch (b=1, "
-                            f"guidance {guidance} through timestep_cond), {FRAMES}-frame windows 512x512 (latent {args.latent}x{args.latent}), "
+            "config": workload_config(args, parallelism=par_desc) if not c3 else {
+                "workload": f"config 3: SD1.5 UNet3D{' (time_cond_proj_dim 256)' if lcm else ''} + motion modules + 4 ControlNets {cond_scale}, "
+                            + (f"LCM branch (b=1, guidance {guidance} through timestep_cond), " if lcm else f"CFG {guidance} (b=2), ")
+                            + f"{FRAMES}-frame windows 512x512 (latent {args.latent}x{args.latent}), "
                             f"{n_steps} steps; one bench step = one denoising step; scheduler arithmetic = DDIM update (the LCM scheduler is "
                             "outside the hot path)", "frames_per_window": FRAMES, "steps": n_steps, "controlnets": n_nets,
                 "cond_scale": cond_scale, "parallelism": par_desc, "window_overlap_frames": OVERLAP},
@@ -492,7 +494,7 @@ def run_b200(args):
                           + ((1280, 4),) * 2 + ((1280, 8),) * 4) * rows_cn * 2
             line["nvlink_bytes_per_step_per_unet_rank"] = per_net * n_nets
         extra = {}
-        if args.eager_yardstick and world == 1 and not lcm:
+        if args.eager_yardstick and world == 1 and not c3:
             del loop, unet, nets, mc
             torch.cuda.empty_cache()
             try:
@@ -501,7 +503,7 @@ def run_b200(args):
                 extra["torch_eager_gpu"] = {"error": f"{type(e).__name__}: {e}"[:200]}
         if extra:
             line["extra"] = extra
-        if args.cpu_baseline and world == 1 and not lcm:
+        if args.cpu_baseline and world == 1 and not c3:
             step, desc, kind = cpu_reference_step_factory(args.cpu_frames, args.latent)
             t0 = time.perf_counter()
             step()
@@ -522,7 +524,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--latent", type=int, default=LATENT)
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames of the bounded CPU sample (>= 4: temporal attention is real)")
-    ap.add_argument("--workload", default="config2", choices=["config2", "config3"],
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config3-cfg"],
                     help="config2 = the headline (BASELINE configs[1]); config3 = LCM + 4 ControlNets, 4 steps (configs[2])")
     ap.add_argument("--windows", type=int, default=0, help="clip layout: UNet ranks = windows of the clip (default: 5 of 8 ranks, "
                     "else half the ranks); the other ranks serve ControlNet jobs")
