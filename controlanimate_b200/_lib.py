@@ -35,6 +35,7 @@ SIGNATURES = {
     "ca_upsample_nearest": (_i, [_vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ca_concat_channels": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
     "ca_row_stats": (_i, [_vp, _vp, _ll, _i, _ll, _f, _i, _vp]),
+    "ca_cfg_ddim_step": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _f, _f, _f, _f, _f, _i, _i, _vp]),
     "ca_linear_ln": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _ll, _i, _i, _ll, _ll, _i, _i, _vp]),
 }
 

@@ -436,6 +436,34 @@ def concat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def cfg_ddim_step(model_out: torch.Tensor, latents: torch.Tensor, guidance_scale: Optional[float],
+                  coefficients: Sequence[float], *, out: Optional[torch.Tensor] = None,
+                  noise_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Guidance combine + DDIM update of one denoising step in one launch (ca_cfg_ddim_step; reference
+    controlanimation_pipeline.py:841-849).  model_out: the UNet output, [2, ...] = [uncond, cond] rows when guidance_scale
+    is given, else [1, ...]; latents [1, ...] (any of bf16 / f16 / f32); coefficients = DDIMScheduler.coefficients(t) =
+    (sqrt a_t, sqrt(1 - a_t), sqrt a_prev, sqrt(1 - a_prev)).  Returns the new latents (`out`, which may be `latents`)."""
+    _cuda(model_out, latents, out, noise_out)
+    cfg = guidance_scale is not None
+    n = latents.numel()
+    if model_out.numel() != (2 if cfg else 1) * n or model_out.shape[1:] != latents.shape[1:]:
+        raise ValueError(f"cfg_ddim_step: model_out {tuple(model_out.shape)} does not match latents {tuple(latents.shape)} "
+                         f"({'two CFG rows' if cfg else 'one row'} expected)")
+    if not (model_out.is_contiguous() and latents.is_contiguous()):
+        raise ValueError("cfg_ddim_step: model_out and latents must be contiguous")
+    if out is None:
+        out = torch.empty_like(latents)
+    for o in (out, noise_out):
+        if o is not None and (o.shape != latents.shape or o.dtype != latents.dtype or not o.is_contiguous()):
+            raise ValueError("cfg_ddim_step: out / noise_out must look like latents")
+    sa, s1a, sp, s1p = (float(c) for c in coefficients)
+    with P.span("loop_update", 1, float(model_out.numel() * model_out.element_size() + 2 * n * latents.element_size())):
+        L.check(L.load().ca_cfg_ddim_step(model_out.data_ptr(), latents.data_ptr(), out.data_ptr(), _ptr(noise_out), n,
+                                          int(cfg), float(guidance_scale) if cfg else 0.0, sa, s1a, sp, s1p, _dt(model_out),
+                                          _dt(latents), _stream()), "ca_cfg_ddim_step")
+    return out
+
+
 def spatial_attention_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, frames: int, sites: int, heads: int,
                            scale: Optional[float] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """softmax(q k^T scale) v over the sites of each frame, per head (ca_spatial_attn_core).  q / k / v: [frames * sites, C]

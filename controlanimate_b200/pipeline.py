@@ -161,6 +161,7 @@ class DenoisingLoop:
         if use_lcm and parallel is not None and parallel.halves == 2:
             raise ValueError("the LCM branch has no CFG halves to split")
         self.use_cuda_graph = use_cuda_graph
+        self.fused_update = True   # step(): guidance combine + DDIM update as one kernel (ca_cfg_ddim_step) instead of torch ops
         self._graphs = {}
         self.parallel = parallel
         self._transport = None
@@ -189,6 +190,14 @@ class DenoisingLoop:
         if self.parallel is not None:
             local = self._local_noise(latents, t, prompt_embeds)
             return self.parallel.combine_noise(local, latents, self.guidance_scale)
+        noise = self._model_out(latents, t, prompt_embeds).to(latents.dtype)                             # :841
+        if self.do_cfg:
+            u, c = noise.chunk(2)
+            noise = u + self.guidance_scale * (c - u)                                                    # :845-846
+        return noise
+
+    def _model_out(self, latents: torch.Tensor, t, prompt_embeds: torch.Tensor) -> torch.Tensor:
+        """The UNet output of one step in the model dtype, rows [uncond, cond] with CFG (ControlNets -> kernel (3) -> UNet3D)."""
         f = latents.shape[2]
         cfg = self.do_cfg
         model_in = torch.cat([latents] * 2) if cfg else latents                                          # :797
@@ -198,13 +207,8 @@ class DenoisingLoop:
             down, mid = self.controlnets(model_in[-1:] if single else model_in, t,
                                          prompt_embeds[-1:] if single else prompt_embeds, f,
                                          do_classifier_free_guidance=cfg, guess_mode=self.guess_mode)
-        noise = self.unet(model_in, t, encoder_hidden_states=prompt_embeds, down_block_additional_residuals=down,
-                          mid_block_additional_residual=mid, timestep_cond=self._w_embedding(model_in)
-                          ).sample.to(latents.dtype)                                                     # :823-841
-        if cfg:
-            u, c = noise.chunk(2)
-            noise = u + self.guidance_scale * (c - u)                                                    # :845-846
-        return noise
+        return self.unet(model_in, t, encoder_hidden_states=prompt_embeds, down_block_additional_residuals=down,
+                         mid_block_additional_residual=mid, timestep_cond=self._w_embedding(model_in)).sample   # :823-841
 
     def invalidate_graphs(self):
         """Drop every captured graph (call after swapping modules, e.g. install() / set_ip_adapter)."""
@@ -283,7 +287,9 @@ class DenoisingLoop:
         return self.unet(model_in, t, encoder_hidden_states=prompt, down_block_additional_residuals=down,
                          timestep_cond=self._w_embedding(model_in)).sample.to(latents.dtype)
 
-    def _graphed_noise(self, latents, t: int, prompt_embeds):
+    def _graphed_noise(self, latents, t: int, prompt_embeds, raw: bool = False):
+        """Replay (capturing first) this step's noise prediction.  raw: return the UNet output before `.to(latents.dtype)` and
+        the guidance combine (the fused update kernel of `step` consumes it)."""
         mc = self.controlnets
         images = list(mc.prep_images) if mc is not None and mc.prep_images is not None else []
         # everything the captured kernels read by value or by baked-in pointer is part of the key: shapes, the scalars of
@@ -291,7 +297,7 @@ class DenoisingLoop:
         key = (tuple(latents.shape), latents.dtype, tuple(prompt_embeds.shape), prompt_embeds.dtype, latents.device,
                float(self.guidance_scale), bool(self.guess_mode), tuple(mc.cond_scale) if mc is not None else (),
                (bool(mc.lazy), bool(mc.overlap)) if mc is not None else None, tuple((tuple(im.shape), im.dtype) for im in images),
-               self._weight_stamp())
+               self._weight_stamp(), bool(raw))
         g = self._graphs.get(key)
         if g is None:
             if len(self._graphs) >= 4:          # stale captures pin their private memory pools
@@ -305,7 +311,7 @@ class DenoisingLoop:
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
                 # with step parallelism only this rank's share is captured; the (tiny) all-gather + CFG combine stay eager
-                fn = self.predict_noise if self.parallel is None else self._local_noise
+                fn = self._local_noise if self.parallel is not None else (self._model_out if raw else self.predict_noise)
                 with torch.cuda.stream(side):                # warm-up: cuDNN algorithm selection, caches, workspaces
                     for _ in range(2):
                         fn(s_lat, s_t, s_prompt)
@@ -335,10 +341,21 @@ class DenoisingLoop:
     @torch.no_grad()
     def step(self, latents: torch.Tensor, t: int, prompt_embeds: torch.Tensor) -> torch.Tensor:
         """latents [1,4,f,h,w] (fp32 or model dtype), prompt_embeds [2,L,D] = [negative, positive] when CFG."""
+        fused = self.fused_update and latents.is_cuda and latents.is_contiguous() and type(self.scheduler) is DDIMScheduler
+        if fused and self.parallel is None:
+            # N4: `.to(latents_dtype)`, the guidance combine and the scheduler step as one launch on the raw UNet output
+            from . import ops
+            raw = self._graphed_noise(latents, t, prompt_embeds, raw=True) if self.use_cuda_graph else \
+                self._model_out(latents, t, prompt_embeds)
+            return ops.cfg_ddim_step(raw, latents, self.guidance_scale if self.do_cfg else None,
+                                     self.scheduler.coefficients(int(t)))                                # :841-849
         if self.use_cuda_graph:
             noise = self._graphed_noise(latents, t, prompt_embeds)
         else:
             noise = self.predict_noise(latents, t, prompt_embeds)
+        if fused and noise.is_contiguous() and noise.shape == latents.shape:
+            from . import ops
+            return ops.cfg_ddim_step(noise, latents, None, self.scheduler.coefficients(int(t)))          # :849
         return self.scheduler.step(noise, int(t), latents)                                               # :849
 
     @torch.no_grad()

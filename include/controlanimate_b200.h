@@ -194,6 +194,21 @@ int ca_upsample_nearest(const void* x, void* y, long long n, int c, int in_h, in
                         int dtype, void* stream);
 int ca_concat_channels(const void* a, const void* b, void* y, long long rows, int ca, int cb, int dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Loop glue: classifier-free-guidance combine + DDIM update of one step in ONE launch.
+ * Replaces `noise_pred.to(latents_dtype)`, `noise_pred_uncond + guidance_scale * (noise_pred_text - noise_pred_uncond)`
+ * (animatediff/pipelines/controlanimation_pipeline.py:841, 845-846) and `scheduler.step(...).prev_sample` (:849; diffusers
+ * 0.23.0 DDIMScheduler.step with eta = 0, epsilon prediction, clip_sample False — third party, restated):
+ *     eps = cfg ? u + guidance * (c - u) : model_out;  x0 = (x - sqrt(1 - a_t) eps) / sqrt(a_t);
+ *     latents_out = sqrt(a_prev) x0 + sqrt(1 - a_prev) eps
+ *   model_out   [cfg ? 2n : n] elements of `model_dtype`, dense: the UNet output rows [uncond | cond]
+ *   latents     [n] elements of `latent_dtype`; latents_out [n] (may alias latents); noise_out [n] or NULL (the guided eps)
+ *   fp32 arithmetic; model_out is first rounded to latent_dtype as the reference's `.to(latents_dtype)` does
+ * ------------------------------------------------------------------------------------------- */
+int ca_cfg_ddim_step(const void* model_out, const void* latents, void* latents_out, void* noise_out, long long n, int cfg,
+                     float guidance, float sqrt_alpha_t, float sqrt_one_minus_alpha_t, float sqrt_alpha_prev,
+                     float sqrt_one_minus_alpha_prev, int model_dtype, int latent_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

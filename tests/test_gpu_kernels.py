@@ -523,3 +523,38 @@ def test_spatial_attention_core(ops, frames, sites, heads, hd, mag, dtype):
     g = qkv.cuda()
     o = ops.spatial_attention_core(g[:, :c], g[:, c:2 * c], g[:, 2 * c:], frames=frames, sites=sites, heads=heads)
     assert relerr(o, ref) <= 2 * REL[dtype]          # P is rounded to the storage type before P V, like every flash kernel
+
+
+@pytest.mark.parametrize("lat_dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("model_dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape,cfg,t", [((1, 4, 16, 64, 64), True, 951), ((1, 4, 3, 7, 5), True, 51), ((1, 4, 8, 12, 7), False, 501),
+                                         ((1, 4, 2, 6, 6), True, 1)])
+def test_cfg_ddim_step(ops, shape, cfg, t, model_dtype, lat_dtype):
+    """ca_cfg_ddim_step == `.to(latents_dtype)` + `u + g (c - u)` (controlanimation_pipeline.py:841, 845-846) + the oracle's
+    eta-0 DDIM update (:849; diffusers DDIMScheduler, third party -> parity unpinned) on the same rounded inputs; ragged
+    element counts, the last step (prev alpha = 1), in place."""
+    from controlanimate_b200.pipeline import DDIMScheduler
+    g = 7.5
+    rows = 2 if cfg else 1
+    out = synth.tensor(71, f"dd.o.{shape}.{t}", (rows,) + shape[1:]).to(model_dtype)
+    lat = synth.tensor(71, f"dd.x.{shape}.{t}", shape).to(lat_dtype)
+    eps = out.to(lat_dtype).float()
+    if cfg:
+        eps = eps[:1] + g * (eps[1:] - eps[:1])
+    ref = R.ddim_step(eps, t, lat.float(), R.ddim_alphas_cumprod(), 20)
+    sched = DDIMScheduler()
+    sched.set_timesteps(20)
+    noise = torch.empty_like(lat, device="cuda")
+    x = lat.cuda()
+    y = ops.cfg_ddim_step(out.cuda(), x, g if cfg else None, sched.coefficients(t), noise_out=noise)
+    assert y.dtype == lat_dtype and y.shape == lat.shape and torch.equal(x.cpu(), lat)     # input untouched
+    assert relerr(y, ref) <= REL[lat_dtype]
+    assert relerr(noise, eps) <= REL[lat_dtype]
+    plain = float((y.float().cpu() - ref).abs().max() / ref.abs().max())
+    print(f"cfg_ddim_step {shape} cfg={cfg} t={t} {model_dtype}->{lat_dtype}: plain relative error {plain:.2e}")
+    z = ops.cfg_ddim_step(out.cuda(), x, g if cfg else None, sched.coefficients(t), out=x)  # in place
+    assert z.data_ptr() == x.data_ptr() and torch.equal(z, y)
+    with pytest.raises(ValueError):
+        ops.cfg_ddim_step(out.cuda()[:1], x, g, sched.coefficients(t))                      # CFG needs two rows
+    with pytest.raises(ValueError):
+        ops.cfg_ddim_step(out.cuda(), x.transpose(3, 4), g if cfg else None, sched.coefficients(t))

@@ -245,6 +245,38 @@ def test_cuda_graph_replay_matches_eager_and_is_deterministic(ca):
     assert len(graphed._graphs) == 1 and not torch.equal(b[0], b[1])     # timestep really changes inside the replayed graph
 
 
+def test_fused_loop_update_matches_torch_ops(ca):
+    """DenoisingLoop.step with the one-launch guidance + DDIM update (ca_cfg_ddim_step, the default) against the same step
+    with the torch elementwise ops it replaces (controlanimation_pipeline.py:841-849), eager and captured, CFG and LCM (b = 1)."""
+    cfg = small_cfg()
+    cfg["time_cond_proj_dim"] = 256
+    f, hh = 4, 16
+    unet = ca.unet.UNet3DConditionModel(**cfg)
+    load_synth(unet, U.unet3d_shapes(cfg), SEED)
+    unet = unet.cuda().bfloat16().eval()
+    sched = ca.pipeline.DDIMScheduler()
+    ts = sched.set_timesteps(4)
+    lat = synth.tensor(SEED, "fu.lat", (1, 4, f, hh, hh)).cuda()
+    for lcm in (False, True):
+        prompt = synth.tensor(SEED, "fu.ctx", (1 if lcm else 2, 7, cfg["cross_attention_dim"])).cuda().bfloat16()
+        for graph in (False, True):
+            a = ca.pipeline.DenoisingLoop(unet, None, sched, guidance_scale=7.5, use_cuda_graph=graph, use_lcm=lcm)
+            b = ca.pipeline.DenoisingLoop(unet, None, sched, guidance_scale=7.5, use_cuda_graph=graph, use_lcm=lcm)
+            b.fused_update = False
+            for t in ts[:2]:
+                x, y = a.step(lat, t, prompt), b.step(lat, t, prompt)
+                assert x.dtype == y.dtype == lat.dtype and x.shape == y.shape
+                # same operands, fp32 on both sides: only the association of the four scheduler terms differs
+                assert float((x - y).abs().max()) <= 2e-5 * float(y.abs().max()), (lcm, graph, t)
+    half = lat.bfloat16()                                              # 16-bit latents (the reference's fp16 GPU path)
+    a = ca.pipeline.DenoisingLoop(unet, None, sched, guidance_scale=7.5)
+    b = ca.pipeline.DenoisingLoop(unet, None, sched, guidance_scale=7.5)
+    b.fused_update = False
+    prompt = synth.tensor(SEED, "fu.ctx", (2, 7, cfg["cross_attention_dim"])).cuda().bfloat16()
+    x, y = a.step(half, ts[0], prompt), b.step(half, ts[0], prompt)
+    assert x.dtype == torch.bfloat16 and cosine(x, y) >= 0.9999       # torch rounds after every op, the kernel once
+
+
 def test_controlnets_on_their_own_streams_match_single_stream(ca):
     """MultiControlNetResiduals.overlap: every ControlNet on its own CUDA stream next to the UNet encoder, joined by the
     first skip add.  Same kernels on the same data: the step must equal the single-stream one, eager and captured."""
