@@ -80,6 +80,36 @@ class MultiControlNetResiduals:
         self.overlap = False
         self._streams: List[torch.cuda.Stream] = []
         self._pending = None
+        # hoist_cond_embedding: `controlnet_cond_embedding(image)` (eight convolutions at up to full image resolution per net)
+        # depends on the prepared control video only, which is fixed for all steps of a window: evaluate it once per
+        # (net, images) instead of once per step as diffusers does.  Same arithmetic on the same operands; off by default so
+        # that a step of this class does exactly the work of a reference step.
+        self.hoist_cond_embedding = False
+        self._cond_cache = {}
+
+    def cond_embedding(self, k: int, image: torch.Tensor, into: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The hoisted conditioning embedding of net k for `image`: one cache entry per (net, image buffer), recomputed when
+        the buffer's contents (version counter), shape or the embedding weights changed.  `into`: a caller-owned buffer the
+        value must live in (a captured CUDA graph reads the embedding through a baked-in pointer)."""
+        net = self.controlnets[k]
+        # the entry HOLDS the image's storage owner: while it is cached its address cannot be recycled for another window's
+        # images, so (owner identity, address, version) cannot hit stale contents
+        owner = image._base if image._base is not None else image
+        slot = (k, image.data_ptr(), tuple(image.shape), image.dtype)
+        ident = (image._version, tuple((p.data_ptr(), p._version) for p in net.controlnet_cond_embedding.parameters()))
+        ent = self._cond_cache.get(slot)
+        if ent is not None and ent[0] == ident and ent[2] is owner and (into is None or ent[1] is into):
+            return ent[1]
+        if image.is_cuda and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("the hoisted ControlNet conditioning embedding must be evaluated before the graph capture")
+        val = net.embed_condition(image)
+        if into is not None:
+            into.copy_(val)
+            val = into
+        if len(self._cond_cache) >= 64 and slot not in self._cond_cache:      # image buffers come and go with the windows
+            self._cond_cache.clear()
+        self._cond_cache[slot] = (ident, val, owner)
+        return val
 
     def raw(self, control_model_input, t, controlnet_prompt_embeds, frame_count, nets=None, images=None, out=None,
             sample_offset: int = 0):
@@ -95,9 +125,11 @@ class MultiControlNetResiduals:
         ctx_map = (sample_offset + torch.arange(b * frame_count, device=x.device)) % n_prompts
         nets = list(range(len(self.controlnets))) if nets is None else list(nets)
         images = self.prep_images if images is None else images
+        hoisted = {k: self.cond_embedding(k, images[k]) for k in nets} if self.hoist_cond_embedding else {}
         if not (self.overlap and self.lazy and x.is_cuda):
             return [self.controlnets[k](x, t, controlnet_prompt_embeds, images[k], ctx_map=ctx_map,
-                                        out=None if out is None else out[j]) for j, k in enumerate(nets)]
+                                        out=None if out is None else out[j], cond_embedding=hoisted.get(k))
+                    for j, k in enumerate(nets)]
         from .layers import _ctx_i32
         _ctx_i32(ctx_map)        # shared by every net: convert on the caller's stream, BEFORE the fork (the nets only hit the cache)
         main = torch.cuda.current_stream(x.device)
@@ -111,7 +143,7 @@ class MultiControlNetResiduals:
             side.wait_event(fork)
             with torch.cuda.stream(side):
                 per_net.append(self.controlnets[k](x, t, controlnet_prompt_embeds, images[k], ctx_map=ctx_map,
-                                                   out=None if out is None else out[j]))
+                                                   out=None if out is None else out[j], cond_embedding=hoisted.get(k)))
                 ev = torch.cuda.Event()
                 ev.record(side)
                 events.append(ev)
@@ -296,9 +328,13 @@ class DenoisingLoop:
         # the step, and the weights; the per-window control images are copied into graph-owned buffers before a replay
         key = (tuple(latents.shape), latents.dtype, tuple(prompt_embeds.shape), prompt_embeds.dtype, latents.device,
                float(self.guidance_scale), bool(self.guess_mode), tuple(mc.cond_scale) if mc is not None else (),
-               (bool(mc.lazy), bool(mc.overlap)) if mc is not None else None, tuple((tuple(im.shape), im.dtype) for im in images),
+               (bool(mc.lazy), bool(mc.overlap), bool(mc.hoist_cond_embedding)) if mc is not None else None,
+               tuple((tuple(im.shape), im.dtype) for im in images),
                self._weight_stamp(), bool(raw))
         g = self._graphs.get(key)
+        if mc is not None and mc.hoist_cond_embedding and self.parallel is not None:
+            raise ValueError("hoisted conditioning embeddings are not wired into the captured step-parallel paths "
+                             "(use them eagerly there, or capture without them)")
         if g is None:
             if len(self._graphs) >= 4:          # stale captures pin their private memory pools
                 self._graphs.clear()
@@ -322,16 +358,22 @@ class DenoisingLoop:
             finally:
                 if mc is not None:
                     mc.prep_images = images if images else None
+            # the capture baked in the pointers of the hoisted conditioning embeddings the warm-up passes left in mc's cache:
+            # the graph keeps them alive and refreshes them in place when a window's images change
+            emb = [mc.cond_embedding(k, im) for k, im in enumerate(s_images)] if mc is not None and mc.hoist_cond_embedding else None
             g = self._graphs[key] = dict(graph=graph, lat=s_lat, t=s_t, prompt=s_prompt, out=s_out, images=s_images,
-                                         seen=[None] * len(s_images))
+                                         seen=[None] * len(s_images), emb=emb)
         g["lat"].copy_(latents, non_blocking=True)
         if prompt_embeds.data_ptr() != g["prompt"].data_ptr():
             g["prompt"].copy_(prompt_embeds, non_blocking=True)
         for k, im in enumerate(images):      # the reference re-runs prep_control_images for every window (pipeline :226-273)
-            ident = (im.data_ptr(), im._version)
-            if g["seen"][k] != ident:
+            seen = g["seen"][k]      # (tensor, version): holding the tensor keeps its address from being recycled unnoticed
+            if seen is None or seen[0] is not im or seen[1] != im._version:
                 g["images"][k].copy_(im, non_blocking=True)
-                g["seen"][k] = ident
+                g["seen"][k] = (im, im._version)
+        if g["emb"] is not None:             # (no-op unless the images above changed or another loop used mc in between)
+            for k, buf in enumerate(g["emb"]):
+                mc.cond_embedding(k, g["images"][k], into=buf)
         g["t"].fill_(int(t))
         g["graph"].replay()
         if self.parallel is not None:
@@ -469,6 +511,9 @@ class ClipLoop:
             if self._graph is not None and self._graph["key"] != key:
                 raise ValueError("ClipLoop: the captured step was recorded for other input shapes; build a new loop (the capture "
                                  "is collective: every rank would have to re-record at the same step)")
+            if self.mc.hoist_cond_embedding:
+                raise ValueError("ClipLoop: hoisted conditioning embeddings are not wired into the captured clip step "
+                                 "(run it eagerly, or capture without them)")
             if self._graph is None:
                 dev = self.unet.conv_in.weight.device
                 s_t = torch.full((1,), int(t), dtype=torch.int64, device=dev)

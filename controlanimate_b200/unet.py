@@ -330,8 +330,20 @@ class ControlNetModel(nn.Module):
         y = ops.linear(Ly.tokens(Ly._cl(x4)), conv.weight.reshape(c, c), Ly.f32(conv.bias), out=out)   # 1x1 conv == token GEMM
         return Ly.from_tokens(y, n, h, w)
 
+    def embed_condition(self, controlnet_cond: torch.Tensor) -> torch.Tensor:
+        """`controlnet_cond_embedding(controlnet_cond)` WITHOUT conv_out's bias, channels_last [(b f), boc[0], h, w].  It depends
+        on the prepared control video and the weights only — not on the latents or the timestep — so a caller that denoises the
+        same window for many steps may compute it once per window and pass it to `forward(cond_embedding=...)`
+        (`MultiControlNetResiduals.hoist_cond_embedding`); the reference (diffusers) re-evaluates it inside every step."""
+        dtype = self.conv_in.weight.dtype
+        ce = self.controlnet_cond_embedding
+        c = Ly.conv_bias(ce.conv_in, Ly._cl(controlnet_cond.to(dtype)), silu=True)         # conv -> +bias -> SiLU: one epilogue
+        for blk in ce.blocks:
+            c = Ly.conv_bias(blk, c, silu=True)
+        return Ly._cl(Ly.conv_nobias(ce.conv_out, c))
+
     def forward(self, sample, timestep, encoder_hidden_states, controlnet_cond, ctx_map=None,
-                out: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+                out: Optional[Sequence[torch.Tensor]] = None, cond_embedding: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
         dtype = self.conv_in.weight.dtype
         n = sample.shape[0]
         if not torch.is_tensor(timestep):
@@ -343,12 +355,18 @@ class ControlNetModel(nn.Module):
         resnets = [r for blk in self.down_blocks for r in blk.resnets] + list(self.mid_block.resnets)
         shifts = iter(self._temb_bank.shifts(resnets, emb))
         ce = self.controlnet_cond_embedding
-        c = Ly.conv_bias(ce.conv_in, Ly._cl(controlnet_cond.to(dtype)), silu=True)         # conv -> +bias -> SiLU: one epilogue
-        for blk in ce.blocks:
-            c = Ly.conv_bias(blk, c, silu=True)
-        # conv_in(sample) + conv_out(c): both biases and the sum in one epilogue pass
-        x = Ly.conv_bias(ce.conv_out, c, residual=Ly._cl(Ly.conv_nobias(self.conv_in, Ly._cl(sample.to(dtype)))),
-                         extra_bias=self.conv_in.bias)
+        if cond_embedding is not None:
+            if cond_embedding.shape[0] != n or cond_embedding.dtype != dtype:
+                raise ValueError("cond_embedding must be embed_condition() of this call's control images")
+            # conv_in(sample) + (hoisted) conv_out(c): both biases and the sum in one epilogue pass
+            x = Ly.conv_bias(self.conv_in, Ly._cl(sample.to(dtype)), residual=cond_embedding, extra_bias=ce.conv_out.bias)
+        else:
+            c = Ly.conv_bias(ce.conv_in, Ly._cl(controlnet_cond.to(dtype)), silu=True)     # conv -> +bias -> SiLU: one epilogue
+            for blk in ce.blocks:
+                c = Ly.conv_bias(blk, c, silu=True)
+            # conv_in(sample) + conv_out(c): both biases and the sum in one epilogue pass
+            x = Ly.conv_bias(ce.conv_out, c, residual=Ly._cl(Ly.conv_nobias(self.conv_in, Ly._cl(sample.to(dtype)))),
+                             extra_bias=self.conv_in.bias)
         frames = 1  # every frame is an independent image here: per-frame GroupNorm statistics
         # the temb rows are per frame already (n rows), so the "batch" of the video view is n
         skips = [x]

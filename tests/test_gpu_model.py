@@ -277,6 +277,54 @@ def test_fused_loop_update_matches_torch_ops(ca):
     assert x.dtype == torch.bfloat16 and cosine(x, y) >= 0.9999       # torch rounds after every op, the kernel once
 
 
+def test_hoisted_cond_embedding_matches_per_step_evaluation(ca):
+    """MultiControlNetResiduals.hoist_cond_embedding: `controlnet_cond_embedding(image)` evaluated once per (net, image buffer)
+    instead of once per step (diffusers ControlNetModel.forward; third party).  Same operands, same kernels: the step must
+    equal the per-step evaluation, eager and captured, and must follow a change of the control images (in place and by
+    swapping the buffers) — the captured graph reads the embedding through a baked-in pointer."""
+    cfg = small_cfg()
+    f, hh = 4, 16
+    unet = ca.unet.UNet3DConditionModel(**cfg)
+    load_synth(unet, U.unet3d_shapes(cfg), SEED)
+    unet = unet.cuda().bfloat16().eval()
+    nets = []
+    for k in range(2):
+        cn = ca.unet.ControlNetModel(block_out_channels=cfg["block_out_channels"], cross_attention_dim=cfg["cross_attention_dim"])
+        load_synth(cn, U.controlnet_shapes(cfg), SEED + 1 + k)
+        nets.append(cn.cuda().bfloat16().eval())
+    img = lambda tag: [synth.tensor(SEED, f"h.{tag}{k}", (2 * f, 3, hh * 8, hh * 8), 0.5).cuda().bfloat16() for k in range(2)]
+    first, second = img("a"), img("b")
+    sched = ca.pipeline.DDIMScheduler()
+    ts = sched.set_timesteps(4)
+    lat = synth.tensor(SEED, "h.lat", (1, 4, f, hh, hh)).cuda()
+    prompt = synth.tensor(SEED, "h.ctx", (2, 7, cfg["cross_attention_dim"])).cuda().bfloat16()
+
+    def run(hoist, graph):
+        mc = ca.pipeline.MultiControlNetResiduals(nets, [0.8, 0.4])
+        mc.hoist_cond_embedding = hoist
+        loop = ca.pipeline.DenoisingLoop(unet, mc, sched, guidance_scale=7.5, use_cuda_graph=graph)
+        outs = []
+        mc.prep_images = [im.clone() for im in first]
+        outs += [loop.step(lat, t, prompt).clone() for t in ts[:2]]
+        for dst, src in zip(mc.prep_images, second):                 # next window written into the same buffers
+            dst.copy_(src)
+        outs += [loop.step(lat, t, prompt).clone() for t in ts[:2]]
+        mc.prep_images = [im.clone() for im in first]                # ... and new buffers altogether
+        outs += [loop.step(lat, t, prompt).clone() for t in ts[:2]]
+        torch.cuda.synchronize()
+        return outs, mc, loop
+
+    base, _, _ = run(False, False)
+    assert cosine(base[0], base[2]) < 0.99999                        # the control images matter, so the checks below are not vacuous
+    for graph in (False, True):
+        got, mc, loop = run(True, graph)
+        for x, y in zip(base, got):
+            assert cosine(x, y) >= 0.99999, graph                    # cuDNN may pick another algorithm under capture
+        assert float((got[0] - got[4]).abs().max()) == 0.0           # same images again -> same result
+        if graph:
+            assert len(loop._graphs) == 1
+
+
 def test_controlnets_on_their_own_streams_match_single_stream(ca):
     """MultiControlNetResiduals.overlap: every ControlNet on its own CUDA stream next to the UNet encoder, joined by the
     first skip add.  Same kernels on the same data: the step must equal the single-stream one, eager and captured."""
