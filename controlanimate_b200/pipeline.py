@@ -383,7 +383,8 @@ class DenoisingLoop:
     @torch.no_grad()
     def step(self, latents: torch.Tensor, t: int, prompt_embeds: torch.Tensor) -> torch.Tensor:
         """latents [1,4,f,h,w] (fp32 or model dtype), prompt_embeds [2,L,D] = [negative, positive] when CFG."""
-        fused = self.fused_update and latents.is_cuda and latents.is_contiguous() and type(self.scheduler) is DDIMScheduler
+        fused = (self.fused_update and latents.is_cuda and latents.is_contiguous() and type(self.scheduler) is DDIMScheduler
+                 and latents.dtype in (torch.float32, torch.bfloat16, torch.float16))
         if fused and self.parallel is None:
             # N4: `.to(latents_dtype)`, the guidance combine and the scheduler step as one launch on the raw UNet output
             from . import ops
