@@ -1,7 +1,6 @@
 set -u
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_model.py -m gpu -q -x -k "hoisted or fused_loop or cuda_graph or denoising_step or own_streams" 2>&1 | tail -8 > gpurun_out/t_loop.log; cat gpurun_out/t_loop.log
-for h in 0 1 0 1; do
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-eager-yardstick --hoist-cond-embedding $h 2> gpurun_out/bench_hoist$h.err > gpurun_out/bench_hoist$h.json; python -c "
-import json;d=json.load(open('gpurun_out/bench_hoist$h.json'));print('hoist $h', d['ms_per_step'], d['e2e']['ms_per_step'], d['cond_embedding'], d['gpu_launches'])"
-done
+( time timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -6 ) > gpurun_out/pytest_verify.log 2>&1
+cat gpurun_out/pytest_verify.log
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
+timeout 900 python bench.py 2> gpurun_out/bench_final.err > gpurun_out/bench_final.json; cut -c1-400 gpurun_out/bench_final.json; tail -3 gpurun_out/bench_final.err
