@@ -188,3 +188,48 @@ def test_fold_layernorm_algebra():
     assert torch.allclose(got, want, atol=2e-4, rtol=1e-4)
     # without a positional-encoding table the shift has one row
     assert ops.fold_layernorm(w, gamma, beta)[2].shape == (1, n)
+
+
+def test_hoisted_cond_embedding_cache_follows_images_and_weights():
+    """MultiControlNetResiduals.cond_embedding (host logic of the hoisted ControlNet conditioning embedding): one evaluation per
+    (net, image buffer); re-evaluated when the buffer is written in place, replaced (even at a recycled address), sliced
+    differently, or when the embedding weights change; `into` pins the value to a caller-owned buffer (CUDA-graph pointer)."""
+    from controlanimate_b200.pipeline import MultiControlNetResiduals
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.controlnet_cond_embedding = torch.nn.Linear(1, 1)
+            self.calls = 0
+
+        def embed_condition(self, image):
+            self.calls += 1
+            return image * float(self.controlnet_cond_embedding.weight.detach().reshape(()))
+
+    net = Net()
+    mc = MultiControlNetResiduals([net], [1.0])
+    img = torch.arange(8.0).reshape(4, 2).clone()
+    a = mc.cond_embedding(0, img)
+    assert net.calls == 1 and mc.cond_embedding(0, img) is a and net.calls == 1          # cached
+    assert mc.cond_embedding(0, img[0:4]) is a and net.calls == 1                         # a full-range view of the same storage
+    img.add_(1.0)                                                                         # next window written in place
+    b = mc.cond_embedding(0, img)
+    assert net.calls == 2 and torch.equal(b, img * float(net.controlnet_cond_embedding.weight.detach()))
+    half = mc.cond_embedding(0, img[2:])                                                  # a CFG half's rows: its own entry
+    assert net.calls == 3 and half.shape[0] == 2 and mc.cond_embedding(0, img[2:]) is half and net.calls == 3
+    with torch.no_grad():
+        net.controlnet_cond_embedding.weight.mul_(2.0)                                    # weights changed in place
+    c = mc.cond_embedding(0, img)
+    assert net.calls == 4 and torch.equal(c, 2 * b)
+    other = img.clone()                                                                   # another buffer with equal contents
+    mc.cond_embedding(0, other)
+    assert net.calls == 5
+    buf = torch.empty_like(c)                                                             # graph-owned destination
+    d = mc.cond_embedding(0, img, into=buf)
+    assert d is buf and net.calls == 6 and torch.equal(buf, c)
+    assert mc.cond_embedding(0, img, into=buf) is buf and net.calls == 6                  # refreshed only when needed
+    img.mul_(3.0)
+    assert mc.cond_embedding(0, img, into=buf) is buf and net.calls == 7 and torch.equal(buf, img * float(net.controlnet_cond_embedding.weight.detach()))
+    # the entry owns the image: a new tensor can not reuse its address while it is cached
+    owner = mc._cond_cache[(0, img.data_ptr(), tuple(img.shape), img.dtype)][2]
+    assert owner is img
