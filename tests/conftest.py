@@ -34,3 +34,18 @@ def golden():
         return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
 
     return load
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Kernel parity tests record, next to the asserted error, the plain (no half-ulp subtraction) numbers of every comparison:
+    dump them where a gpurun call brings them back (gpurun_out/kernel_relerr.tsv), worst first."""
+    mod = sys.modules.get("test_gpu_kernels") or sys.modules.get("tests.test_gpu_kernels")
+    rows = getattr(mod, "PLAIN", None) if mod is not None else None
+    if not rows:
+        return
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "kernel_relerr.tsv"), "w") as fh:
+        fh.write("test\tdtype\tasserted (max|err| - half ulp) / max|ref|\tplain max|err| / max|ref|\tworst per-element |err| / max(|ref|, max|ref|/64)\n")
+        for r in sorted(rows, key=lambda r: -r[3]):
+            fh.write(f"{r[0]}\t{r[1]}\t{(r[2] if r[2] is not None else float('nan')):.3e}\t{r[3]:.3e}\t{r[4]:.3e}\n")

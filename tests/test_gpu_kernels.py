@@ -8,6 +8,8 @@ unavoidable quantisation of writing the result as bf16/f16 (bf16 keeps 8 signifi
 alone costs up to 2^-8 = 3.9e-3 relative; the 2e-3 budget is for the arithmetic).  fp32 storage has
 q = 0 and is held to 2e-5, which pins the arithmetic itself.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -33,15 +35,26 @@ def ops():
 MANT = {torch.bfloat16: 8, torch.float16: 11}
 
 
+PLAIN = []   # (test id, dtype, relerr, plain max-normalised error, worst per-element relative error): see conftest.pytest_sessionfinish
+
+
 def relerr(y, ref):
+    """The asserted number (docstring above).  Next to it two PLAIN numbers — no half-ulp subtraction — are recorded for every
+    call and written to gpurun_out/kernel_relerr.tsv at session end: max|y - ref| / max|ref|, and the worst PER-ELEMENT relative
+    error max(|y - ref| / max(|ref|, max|ref| / 64)) (elements within 1/64 of the largest magnitude are held to their own size)."""
     dt = y.dtype
     y = y.detach().float().cpu()
     assert torch.isfinite(y).all()
     err = (y - ref).abs()
+    top = ref.abs().max().clamp_min(1e-12)
+    PLAIN.append((os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0].split("::", 1)[-1], str(dt).replace("torch.", ""), None,
+                  float(err.max() / top), float((err / ref.abs().clamp_min(top / 64)).max())))
     if dt in MANT:  # half an ulp of the storage type at |ref|
         expo = torch.floor(torch.log2(ref.abs().clamp_min(1e-30)))
         err = (err - 0.5 * torch.pow(2.0, expo - (MANT[dt] - 1)) * 1.0001).clamp_min(0)
-    return float(err.max() / ref.abs().max().clamp_min(1e-12))
+    out = float(err.max() / ref.abs().max().clamp_min(1e-12))
+    PLAIN[-1] = PLAIN[-1][:2] + (out,) + PLAIN[-1][3:]
+    return out
 
 
 def to_layout(x, layout):
