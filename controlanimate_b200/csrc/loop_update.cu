@@ -49,6 +49,10 @@ extern "C" __attribute__((visibility("default"))) int ca_cfg_ddim_step(const voi
   CA_CHECK_ARG(model_out && latents && latents_out, "cfg_ddim_step: null pointer");
   CA_CHECK_ARG(n >= 0 && (cfg == 0 || cfg == 1), "cfg_ddim_step: bad n / cfg");
   CA_CHECK_ARG(sqrt_alpha_t > 0.f, "cfg_ddim_step: sqrt(alpha_t) must be positive");
+  // only latents_out may alias an input (latents: same element, read before written); model_out is read through the
+  // read-only path and noise_out is a second output
+  CA_CHECK_ARG(model_out != latents_out && model_out != noise_out && noise_out != latents && noise_out != latents_out,
+               "cfg_ddim_step: model_out / noise_out must not alias the other buffers (latents_out may alias latents)");
   if (n == 0) return CA_OK;
   const long long blocks = (n + kThreads - 1) / kThreads;
   CA_CHECK_ARG(blocks < (1ll << 31), "cfg_ddim_step: tensor too large");

@@ -570,4 +570,6 @@ def test_cfg_ddim_step(ops, shape, cfg, t, model_dtype, lat_dtype):
     with pytest.raises(ValueError):
         ops.cfg_ddim_step(out.cuda()[:1], x, g, sched.coefficients(t))                      # CFG needs two rows
     with pytest.raises(ValueError):
+        ops.cfg_ddim_step(out.cuda(), x, g if cfg else None, sched.coefficients(t), noise_out=x)   # a second output, not an alias
+    with pytest.raises(ValueError):
         ops.cfg_ddim_step(out.cuda(), x.transpose(3, 4), g if cfg else None, sched.coefficients(t))
