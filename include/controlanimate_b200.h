@@ -4,7 +4,7 @@
  * Drop-in boundary for the three operator interfaces of intellerce/controlanimate's denoising
  * loop.  The reference is pure Python/PyTorch: there is no FFI in it, so each entry
  * point cites the reference *operator* it replaces (paths relative to the reference repo root).
- * Host code (controlanimate_b200/*.py) binds these with ctypes; INTEGRATION.md shows the stub.
+ * Host code (the Python modules under controlanimate_b200/) binds these with ctypes; INTEGRATION.md shows the stub.
  *
  * Conventions
  *   - every function returns ca_status_t (0 = ok) and never throws; ca_last_error() gives the text
